@@ -1,0 +1,148 @@
+/* b2s.h — C ABI of libb2s.so: B200 (sm_100a) kernels for the ORB front-end hot path.
+ *
+ * Drop-in boundary.  Each entry point names the reference
+ * interface (file:line under /root/reference) whose arithmetic it replaces.
+ * Plain pointers and sizes only; no torch types.  All device pointers must be
+ * CUDA device memory on the current device; `stream` is a cudaStream_t passed
+ * as void*.  Every function returns 0 on success, non-zero on error
+ * (b2s_last_error() has the text); nothing throws across the ABI.  All work is
+ * enqueued asynchronously on `stream`; nothing here synchronises the device.
+ *
+ * Batching: a "pair" is one (query frame, train frame) match problem.  Rows of
+ * all pairs are concatenated; `*_off` arrays (device, n_pairs+1 int32) are CSR
+ * offsets into the concatenation.  Descriptors are 32 bytes (ORB), row-major,
+ * buffers 16-byte aligned.
+ *
+ * Packed key: key = (distance << 22) | index, distance in [0,256], index < 2^22.
+ * min(key) == lexicographic (distance, index) minimum == OpenCV's tie rule.
+ * Any key >= 0x80000000 means "none"; outputs use B2S_NONE_KEY for it.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+#define B2S_IDX_BITS 22
+#define B2S_IDX_MASK ((1u << B2S_IDX_BITS) - 1u)
+#define B2S_NONE_KEY 0xFFFFFFFFu
+#define B2S_DESC_BYTES 32
+#define B2S_MAX_ROWS_PER_PAIR (1 << B2S_IDX_BITS)
+#define B2S_SELECT_MAX_QUERIES 32768 /* per pair, b2s_select_matches */
+
+/* error codes */
+#define B2S_OK 0
+#define B2S_ERR_INVALID 1   /* bad argument */
+#define B2S_ERR_CUDA 2      /* CUDA runtime error (text in b2s_last_error) */
+#define B2S_ERR_UNSUPPORTED 3
+
+/* Hamming kernel variants */
+#define B2S_VARIANT_POPC 0  /* LOP3/POPC integer-pipe kernel (K1) */
+#define B2S_VARIANT_I8MMA 1 /* tcgen05.mma kind::i8 +-1 contraction (K2) */
+
+int b2s_abi_version(void);
+const char* b2s_last_error(void);
+/* sm_count / cc_major / cc_minor / sm clock kHz of the current device. */
+int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* ---- K1/K2: brute-force Hamming kNN-2 + column minimum ------------------------
+ * Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) and the two batchDistance
+ * passes of BFMatcher(crossCheck=True).match (feature_pipeline.py.bak:68,82,84;
+ * persistent_map.py:266; keyframe_manager.py:126,141) and the NumPy matcher's
+ * distance loops (homography.py:12-15, :21-23) — one distance matrix serves both
+ * directions.
+ *   fwd_best[i], fwd_second[i]  (total_nq)  two smallest (dist, trainIdx) keys of query row i
+ *   bwd_best[j]                 (total_nt)  smallest (dist, queryIdx) key of train row j
+ * Indices inside keys are pair-local.  q_src_row/t_src_row (device, n_pairs int32,
+ * or NULL): row in q_desc/t_desc where pair p's descriptors start, when that differs
+ * from the CSR offset — lets many pairs share one descriptor block (relocalization:
+ * every keyframe against the same current frame, persistent_map.py:244-266) while the
+ * outputs stay CSR-addressed.  max_nq/max_nt: upper bounds on any pair's
+ * row counts (host-known; sizes the grid).  t_split: CTAs per query tile along the
+ * train axis (0 = choose automatically); workspace must hold
+ * b2s_hamming_workspace_bytes(total_nq, t_split_max) bytes when t_split != 1. */
+size_t b2s_hamming_workspace_bytes(int total_nq, int t_split);
+int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc,
+                             const int32_t* q_off, const int32_t* t_off,
+                             const int32_t* q_src_row, const int32_t* t_src_row, int n_pairs,
+                             int total_nq, int total_nt, int max_nq, int max_nt,
+                             uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best,
+                             int variant, int t_split, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* Tuning of the POPC kernel (bench sweeps): csa_level 0..3 (8/6/5/4 POPC per
+ * descriptor pair), rows_per_thread in {2,4}, warps in {4,8}.  -1 keeps a field. */
+int b2s_hamming_set_config(int csa_level, int rows_per_thread, int warps);
+int b2s_hamming_get_config(int* csa_level, int* rows_per_thread, int* warps);
+
+/* ---- selection: ratio LUT, cross-check, stable sort, truncate -----------------
+ * Replaces the Python post-processing of ORBFeaturePipeline.match
+ * (feature_pipeline.py.bak:85-94), the emit rule of BFMatcher(crossCheck=True)
+ * and match_orb_descriptors' ratio + symmetry tests (homography.py:16-25).
+ *   use_ratio: keep iff a second neighbour exists and d1 < ratio_lut[d2]
+ *              (ratio_lut: HOST pointer, 257 int32, = ceil(ratio*d2) in float64)
+ *   use_cross: keep iff index(bwd_best[j]) == i
+ *   sort_by_distance: stable sort by distance (ties ascending queryIdx), else ascending queryIdx
+ *   max_matches: > 0 truncates, 0 = keep all
+ *   kp_q/kp_t: optional (total, 2) float32 keypoint coordinates; when both given,
+ *              out_corr[(q_off[p]+k)*4 .. +3] = (x1, y1, x2, y2) of match k
+ *              (matches_to_points, feature_pipeline.py.bak:104-111)
+ * Outputs for pair p live at [q_off[p], q_off[p] + out_count[p]). */
+int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_second,
+                       const uint32_t* bwd_best, const int32_t* q_off, const int32_t* t_off,
+                       int n_pairs, int max_nq, int use_ratio, int use_cross,
+                       const int32_t* ratio_lut_host, int sort_by_distance, int max_matches,
+                       const float* kp_q, const float* kp_t, int32_t* out_q, int32_t* out_t,
+                       int32_t* out_d, float* out_corr, int32_t* out_count, void* stream);
+
+/* ---- K4: batched 8-point minimal solver ---------------------------------------
+ * Replaces the per-iteration body of ransac_essential up to the hypothesis
+ * (homography.py:325-326 -> eight_point_E, :222-248, K^T F K quirk included).
+ * corr: float32 (x1,y1,x2,y2) per correspondence; pair p owns
+ * [c_off[p], c_off[p]+c_count[p]).  For every pair, H hypotheses:
+ *   samples_in != NULL: use samples_in[(p*H+h)*8 .. +7] (seeded host draws, parity mode)
+ *   samples_in == NULL: draw 8 distinct indices on device from (seed, p, h)
+ * samples_out (optional) receives the indices used.  K_host / Kinv_host: HOST
+ * pointers to 9 doubles, row-major (NULL = identity).  E_out: (n_pairs*H*9) doubles.
+ * Pairs with fewer than 8 correspondences get all-zero hypotheses. */
+int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32_t* c_count,
+                            int n_pairs, int H, const int32_t* samples_in, uint64_t seed,
+                            int32_t* samples_out, const double* K_host, const double* Kinv_host,
+                            double* E_out, void* stream);
+
+/* ---- K3: batched Sampson-error hypothesis scoring ------------------------------
+ * Replaces homography.py:328-333 for all hypotheses at once.
+ * counts[p*H+h] = #{m : (x2^T E x1)^2 < th2 * (Ex1_x^2+Ex1_y^2+Etx2_x^2+Etx2_y^2)}
+ * th2_per_pair: optional device array (n_pairs doubles) overriding th2.
+ * precision: 64 (float64, reference arithmetic) or 32. */
+int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int32_t* c_count,
+                             int n_pairs, const double* E, int H, double th2,
+                             const double* th2_per_pair, int precision, int32_t* counts,
+                             void* stream);
+
+/* ---- winner selection + inlier mask --------------------------------------------
+ * Replaces the sequential best/early-exit bookkeeping of homography.py:335-339:
+ * best_h = first h with count > 0.8*M if any, else the lowest h among the
+ * maximum count; -1 when every count is 0.  inlier_mask[c_off[p]+m] = 1 iff
+ * correspondence m is an inlier of hypothesis best_h (float64 arithmetic). */
+int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c_off,
+                      const int32_t* c_count, int n_pairs, const double* E, int H, double th2,
+                      const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
+                      uint8_t* inlier_mask, void* stream);
+
+/* ---- measurement helper ----------------------------------------------------------
+ * Saturates one SM pipe with independent instructions to measure its rate:
+ * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD.
+ * Launches ctas_per_sm*SMs CTAs of 256 threads doing `iters` x 64 instructions per
+ * thread; *ops_out = total thread-level instructions executed (the caller times it). */
+int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,125 @@
+"""ctypes binding of libb2s.so (include/b2s.h).  No fallback: a missing library or a
+missing CUDA device raises — the product never computes on the CPU.
+
+torch is used for exactly three things here: owning device memory, naming the current
+CUDA stream, and (elsewhere) torch.distributed.  No torch op is on the compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+_LIB_NAME = "libb2s.so"
+_lock = threading.Lock()
+_lib = None
+_lib_pid = None
+
+IDX_BITS = 22
+IDX_MASK = (1 << IDX_BITS) - 1
+NONE_KEY = 0xFFFFFFFF
+DESC_BYTES = 32
+SELECT_MAX_QUERIES = 32768
+VARIANT_POPC = 0
+VARIANT_I8MMA = 1
+
+PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "imad": 6}
+
+
+class B2SError(RuntimeError):
+    """libb2s returned a non-zero status."""
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / _LIB_NAME
+
+
+def _declare(lib):
+    vp, i32, u64, sz, dbl = C.c_void_p, C.c_int, C.c_uint64, C.c_size_t, C.c_double
+    ip = C.POINTER(C.c_int)
+    lib.b2s_abi_version.restype = i32
+    lib.b2s_abi_version.argtypes = []
+    lib.b2s_last_error.restype = C.c_char_p
+    lib.b2s_last_error.argtypes = []
+    lib.b2s_device_info.restype = i32
+    lib.b2s_device_info.argtypes = [ip, ip, ip, ip]
+    lib.b2s_hamming_workspace_bytes.restype = sz
+    lib.b2s_hamming_workspace_bytes.argtypes = [i32, i32]
+    lib.b2s_hamming_knn2_batched.restype = i32
+    lib.b2s_hamming_knn2_batched.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                             vp, vp, vp, i32, i32, vp, sz, vp]
+    lib.b2s_hamming_set_config.restype = i32
+    lib.b2s_hamming_set_config.argtypes = [i32, i32, i32]
+    lib.b2s_hamming_get_config.restype = i32
+    lib.b2s_hamming_get_config.argtypes = [ip, ip, ip]
+    lib.b2s_select_matches.restype = i32
+    lib.b2s_select_matches.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32,
+                                       vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b2s_eight_point_batched.restype = i32
+    lib.b2s_eight_point_batched.argtypes = [vp, vp, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]
+    lib.b2s_ransac_score_batched.restype = i32
+    lib.b2s_ransac_score_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, i32, vp, vp]
+    lib.b2s_ransac_select.restype = i32
+    lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
+    lib.b2s_pipe_microbench.restype = i32
+    lib.b2s_pipe_microbench.argtypes = [i32, i32, i32, C.POINTER(dbl), vp, vp]
+    return lib
+
+
+EXPORTS = (
+    "b2s_abi_version", "b2s_last_error", "b2s_device_info", "b2s_hamming_workspace_bytes",
+    "b2s_hamming_knn2_batched", "b2s_hamming_set_config", "b2s_hamming_get_config",
+    "b2s_select_matches", "b2s_eight_point_batched", "b2s_ransac_score_batched",
+    "b2s_ransac_select", "b2s_pipe_microbench",
+)
+
+
+def load_library():
+    """dlopen libb2s.so (no CUDA call is made).  Raises if it has not been built."""
+    global _lib, _lib_pid
+    with _lock:
+        if _lib is not None and _lib_pid == os.getpid():
+            return _lib
+        path = lib_path()
+        if not path.exists():
+            raise B2SError(
+                f"{path} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C monocular-visual-slam_b200/csrc`. There is no CPU fallback.")
+        _lib = _declare(C.CDLL(str(path)))
+        _lib_pid = os.getpid()
+        if _lib.b2s_abi_version() != 1:
+            raise B2SError("libb2s.so ABI version mismatch")
+        return _lib
+
+
+def require_cuda():
+    """Import torch lazily and insist on a CUDA device (fork-safe: called on first use only)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise B2SError("b200slam needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def check(status: int):
+    if status != 0:
+        msg = load_library().b2s_last_error().decode("utf-8", "replace")
+        if status == 1:
+            raise ValueError(f"libb2s: {msg}")
+        raise B2SError(f"libb2s error {status}: {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device (or host) pointer of a torch tensor / numpy array, None passes NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,335 @@
+"""Batched device API over libb2s: Hamming kNN-2 -> selection -> 8-point hypotheses ->
+Sampson scoring -> winner + inlier mask, for many frame pairs per launch.
+
+This is the measured API (bench.py); the reference-shaped single-pair interfaces in
+``integration/`` are thin veneers over it.  Tensors are only containers for device
+memory; every computation is a libb2s kernel on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import DESC_BYTES, IDX_BITS, IDX_MASK, NONE_KEY, check, current_stream, ptr
+
+
+def ratio_lut(ratio: float) -> np.ndarray:
+    """keep iff d1 < lut[d2]  ==  float(d1) < ratio * float(d2) in float64
+    (feature_pipeline.py.bak:90, homography.py:16)."""
+    return np.array([math.ceil(float(ratio) * float(d)) for d in range(257)], dtype=np.int32)
+
+
+def _prep_desc(d) -> np.ndarray:
+    """Validate one descriptor block; narrower rows are zero-padded to 32 bytes (padding
+    both sides with zeros leaves every Hamming distance unchanged)."""
+    a = np.asarray(d)
+    if a.ndim != 2 or a.dtype != np.uint8:
+        raise ValueError("descriptors must be a (N, W) uint8 array for the Hamming matcher")
+    if a.shape[1] > DESC_BYTES:
+        raise ValueError(f"descriptor width {a.shape[1]} > {DESC_BYTES} bytes is not supported")
+    if a.shape[1] < DESC_BYTES:
+        a = np.concatenate([a, np.zeros((a.shape[0], DESC_BYTES - a.shape[1]), np.uint8)], axis=1)
+    return np.ascontiguousarray(a)
+
+
+@dataclass
+class PairBatch:
+    """Device-resident CSR batch of (query, train) descriptor sets."""
+    q_desc: "torch.Tensor"
+    t_desc: "torch.Tensor"
+    q_off: "torch.Tensor"
+    t_off: "torch.Tensor"
+    q_off_host: np.ndarray
+    t_off_host: np.ndarray
+    kp_q: "torch.Tensor | None" = None
+    kp_t: "torch.Tensor | None" = None
+    q_src: "torch.Tensor | None" = None
+    t_src: "torch.Tensor | None" = None
+
+    @property
+    def n_pairs(self) -> int:
+        return len(self.q_off_host) - 1
+
+    @property
+    def total_nq(self) -> int:
+        return int(self.q_off_host[-1])
+
+    @property
+    def total_nt(self) -> int:
+        return int(self.t_off_host[-1])
+
+    @property
+    def max_nq(self) -> int:
+        return int(np.diff(self.q_off_host).max()) if self.n_pairs else 0
+
+    @property
+    def max_nt(self) -> int:
+        return int(np.diff(self.t_off_host).max()) if self.n_pairs else 0
+
+    @staticmethod
+    def from_host(q_list: Sequence[np.ndarray], t_list: Sequence[np.ndarray],
+                  kpq_list: Sequence[np.ndarray] | None = None,
+                  kpt_list: Sequence[np.ndarray] | None = None, device=None) -> "PairBatch":
+        torch = _capi.require_cuda()
+        if len(q_list) != len(t_list):
+            raise ValueError("q_list and t_list differ in length")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        q = [_prep_desc(x) for x in q_list]
+        t = [_prep_desc(x) for x in t_list]
+        q_off = np.zeros(len(q) + 1, np.int32)
+        t_off = np.zeros(len(t) + 1, np.int32)
+        np.cumsum([len(x) for x in q], out=q_off[1:])
+        np.cumsum([len(x) for x in t], out=t_off[1:])
+        empty = np.zeros((0, DESC_BYTES), np.uint8)
+
+        def up(arrs, dtype, width):
+            cat = np.concatenate(arrs, axis=0) if arrs else np.zeros((0, width), dtype)
+            if cat.shape[0] == 0:
+                return torch.zeros((1, width), dtype=getattr(torch, np.dtype(dtype).name), device=dev)[:0]
+            return torch.from_numpy(np.ascontiguousarray(cat)).pin_memory().to(dev, non_blocking=True)
+
+        kp_q = kp_t = None
+        if kpq_list is not None and kpt_list is not None:
+            kq = [np.asarray(k, np.float32).reshape(-1, 2) for k in kpq_list]
+            kt = [np.asarray(k, np.float32).reshape(-1, 2) for k in kpt_list]
+            for a, b in zip(kq, q):
+                if len(a) != len(b):
+                    raise ValueError("keypoints / descriptors length mismatch (query)")
+            for a, b in zip(kt, t):
+                if len(a) != len(b):
+                    raise ValueError("keypoints / descriptors length mismatch (train)")
+            kp_q, kp_t = up(kq, np.float32, 2), up(kt, np.float32, 2)
+        return PairBatch(
+            q_desc=up(q or [empty], np.uint8, DESC_BYTES), t_desc=up(t or [empty], np.uint8, DESC_BYTES),
+            q_off=torch.from_numpy(q_off).to(dev), t_off=torch.from_numpy(t_off).to(dev),
+            q_off_host=q_off, t_off_host=t_off, kp_q=kp_q, kp_t=kp_t)
+
+
+@dataclass
+class Keys:
+    fwd_best: "torch.Tensor"
+    fwd_second: "torch.Tensor"
+    bwd_best: "torch.Tensor"
+
+
+@dataclass
+class Selection:
+    out_q: "torch.Tensor"
+    out_t: "torch.Tensor"
+    out_d: "torch.Tensor"
+    count: "torch.Tensor"
+    corr: "torch.Tensor | None"
+
+
+class HammingMatcher:
+    """K1/K2 + selection.  Mirrors cv2.BFMatcher(NORM_HAMMING) knnMatch/match semantics
+    (feature_pipeline.py.bak:68,82,84) on batches."""
+
+    def __init__(self, variant: int = _capi.VARIANT_POPC, t_split: int = 0):
+        self.variant = variant
+        self.t_split = t_split
+        self._lib = _capi.load_library()
+        self._ws = None
+
+    def knn2(self, b: PairBatch) -> Keys:
+        torch = _capi.require_cuda()
+        dev = b.q_desc.device
+        nq, nt = b.total_nq, b.total_nt
+        fb = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        fs = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        bb = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        ws_ptr, ws_bytes = None, 0
+        if self.t_split != 1 and nq > 0:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            want = self.t_split if self.t_split > 1 else max(1, min(64, (4 * sms) // max(1, b.n_pairs)))
+            ws_bytes = int(self._lib.b2s_hamming_workspace_bytes(nq, want))
+            if ws_bytes:
+                if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+                    self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                ws_ptr = self._ws.data_ptr()
+        check(self._lib.b2s_hamming_knn2_batched(
+            ptr(b.q_desc), ptr(b.t_desc), ptr(b.q_off), ptr(b.t_off), ptr(b.q_src), ptr(b.t_src),
+            b.n_pairs, nq, nt, b.max_nq, b.max_nt, ptr(fb), ptr(fs), ptr(bb),
+            self.variant, self.t_split, ws_ptr, ws_bytes, current_stream()))
+        return Keys(fb[:nq], fs[:nq], bb[:nt])
+
+    def select(self, b: PairBatch, k: Keys, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
+               sort_by_distance: bool = True, max_matches: int | None = None,
+               with_corr: bool = False) -> Selection:
+        torch = _capi.require_cuda()
+        dev = b.q_desc.device
+        nq = b.total_nq
+        oq = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        ot = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        od = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev)
+        corr = None
+        if with_corr:
+            if b.kp_q is None or b.kp_t is None:
+                raise ValueError("with_corr needs keypoint coordinates in the batch")
+            corr = torch.empty((max(nq, 1), 4), dtype=torch.float32, device=dev)
+        lut = ratio_lut(ratio) if use_ratio else None
+        check(self._lib.b2s_select_matches(
+            ptr(k.fwd_best), ptr(k.fwd_second), ptr(k.bwd_best), ptr(b.q_off), ptr(b.t_off),
+            b.n_pairs, b.max_nq, int(use_ratio), int(use_cross), ptr(lut), int(sort_by_distance),
+            int(max_matches or 0), ptr(b.kp_q) if with_corr else None, ptr(b.kp_t) if with_corr else None,
+            ptr(oq), ptr(ot), ptr(od), ptr(corr), ptr(cnt), current_stream()))
+        return Selection(oq[:nq], ot[:nq], od[:nq], cnt[:b.n_pairs], None if corr is None else corr[:nq])
+
+    # ---- host convenience: numpy in, numpy out (includes H2D / D2H) -------------------
+    def match_pairs(self, q_list, t_list, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
+                    sort_by_distance: bool = True, max_matches: int | None = None):
+        """-> list of (queryIdx, trainIdx, distance) int32 arrays, one per pair."""
+        torch = _capi.require_cuda()
+        b = PairBatch.from_host(q_list, t_list)
+        if b.n_pairs == 0:
+            return []
+        if b.max_nq > _capi.SELECT_MAX_QUERIES:
+            raise ValueError(f"more than {_capi.SELECT_MAX_QUERIES} query descriptors in one pair")
+        keys = self.knn2(b)
+        sel = self.select(b, keys, use_ratio=use_ratio, use_cross=use_cross, ratio=ratio,
+                          sort_by_distance=sort_by_distance, max_matches=max_matches)
+        packed = torch.stack([sel.out_q, sel.out_t, sel.out_d]).cpu().numpy()
+        cnt = sel.count.cpu().numpy()
+        out = []
+        for p in range(b.n_pairs):
+            o, c = int(b.q_off_host[p]), int(cnt[p])
+            if c < 0:
+                raise _capi.B2SError("select kernel: pair larger than the declared maximum")
+            out.append((packed[0, o:o + c].copy(), packed[1, o:o + c].copy(), packed[2, o:o + c].copy()))
+        return out
+
+    def knn2_pairs(self, q_list, t_list):
+        """-> list of (fwd_best, fwd_second, bwd_best) uint32 packed-key arrays per pair."""
+        b = PairBatch.from_host(q_list, t_list)
+        if b.n_pairs == 0:
+            return []
+        k = self.knn2(b)
+        fb = k.fwd_best.cpu().numpy().view(np.uint32)
+        fs = k.fwd_second.cpu().numpy().view(np.uint32)
+        bb = k.bwd_best.cpu().numpy().view(np.uint32)
+        return [(fb[b.q_off_host[p]:b.q_off_host[p + 1]], fs[b.q_off_host[p]:b.q_off_host[p + 1]],
+                 bb[b.t_off_host[p]:b.t_off_host[p + 1]]) for p in range(b.n_pairs)]
+
+
+class EssentialRansac:
+    """K4 + K3 + winner selection (homography.py:302-345 batched)."""
+
+    def __init__(self):
+        self._lib = _capi.load_library()
+
+    @staticmethod
+    def _k_args(K):
+        if K is None:
+            return None, None, None
+        Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+        Kinv = np.ascontiguousarray(np.linalg.inv(Kd))          # homography.py:228
+        return Kd, Kinv, (Kd, Kinv)
+
+    def hypotheses(self, corr, c_off, c_count, n_pairs: int, H: int, *, samples=None, seed: int = 0,
+                   K=None, return_samples: bool = False):
+        torch = _capi.require_cuda()
+        E = torch.empty((max(n_pairs, 1), max(H, 1), 9), dtype=torch.float64, device=corr.device)
+        s_out = torch.empty((max(n_pairs, 1), max(H, 1), 8), dtype=torch.int32, device=corr.device) if return_samples else None
+        Kd, Kinv, _keep = self._k_args(K)
+        check(self._lib.b2s_eight_point_batched(
+            ptr(corr), ptr(c_off), ptr(c_count), n_pairs, H, ptr(samples), C.c_uint64(seed & (2**64 - 1)),
+            ptr(s_out), ptr(Kd), ptr(Kinv), ptr(E), current_stream()))
+        E = E[:n_pairs, :H]
+        return (E, s_out[:n_pairs, :H]) if return_samples else E
+
+    def score(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, precision: int = 64):
+        torch = _capi.require_cuda()
+        H = E.shape[1]
+        counts = torch.empty((max(n_pairs, 1), max(H, 1)), dtype=torch.int32, device=corr.device)
+        check(self._lib.b2s_ransac_score_batched(
+            ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2), ptr(th2_per_pair),
+            precision, ptr(counts), current_stream()))
+        return counts[:n_pairs, :H]
+
+    def select(self, counts, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None):
+        torch = _capi.require_cuda()
+        H = E.shape[1]
+        best_h = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
+        best_c = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
+        mask = torch.zeros(max(corr.shape[0], 1), dtype=torch.uint8, device=corr.device)
+        check(self._lib.b2s_ransac_select(
+            ptr(counts), ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2),
+            ptr(th2_per_pair), ptr(best_h), ptr(best_c), ptr(mask), current_stream()))
+        return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
+
+
+@dataclass
+class FrontendConfig:
+    """One pass of the hot path.  Defaults = configs/pipeline/kitti_default.json + the
+    north-star's combined matcher (kNN-2 + Lowe ratio + cross-check)."""
+    use_ratio: bool = True
+    use_cross: bool = True
+    ratio: float = 0.8
+    max_matches: int | None = 500
+    hypotheses: int = 2000
+    threshold: float = 0.01
+    precision: int = 64
+    seed: int = 1337
+
+
+@dataclass
+class FrontendResult:
+    keys: Keys
+    sel: Selection
+    E: "torch.Tensor"
+    counts: "torch.Tensor"
+    best_h: "torch.Tensor"
+    best_count: "torch.Tensor"
+    inlier_mask: "torch.Tensor"
+
+
+class Frontend:
+    """match -> select -> hypotheses -> score -> winner, all on the current stream."""
+
+    def __init__(self, cfg: FrontendConfig | None = None, variant: int = _capi.VARIANT_POPC, t_split: int = 0):
+        self.cfg = cfg or FrontendConfig()
+        self.matcher = HammingMatcher(variant=variant, t_split=t_split)
+        self.ransac = EssentialRansac()
+        self.launches_per_run = 0
+
+    def run(self, b: PairBatch, K=None, samples=None) -> FrontendResult:
+        c = self.cfg
+        keys = self.matcher.knn2(b)
+        sel = self.matcher.select(b, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
+                                  sort_by_distance=True, max_matches=c.max_matches, with_corr=True)
+        E = self.ransac.hypotheses(sel.corr, b.q_off, sel.count, b.n_pairs, c.hypotheses,
+                                   samples=samples, seed=c.seed, K=K)
+        th2 = c.threshold ** 2
+        counts = self.ransac.score(sel.corr, b.q_off, sel.count, b.n_pairs, E, th2, precision=c.precision)
+        best_h, best_c, mask = self.ransac.select(counts, sel.corr, b.q_off, sel.count, b.n_pairs, E, th2)
+        return FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
+
+
+def pipe_microbench(which: str, iters: int = 2000, ctas_per_sm: int = 8, repeats: int = 5):
+    """Measured instruction rate of one SM pipe: (thread-instructions/s, per clk per SM
+    at the reported max clock).  Roofline denominator for the POPC kernel."""
+    torch = _capi.require_cuda()
+    lib = _capi.load_library()
+    sink = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ops = C.c_double(0.0)
+    best = float("inf")
+    for r in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.b2s_pipe_microbench(_capi.PIPE_IDS[which], iters, ctas_per_sm, C.byref(ops), ptr(sink), current_stream()))
+        e1.record()
+        e1.synchronize()
+        if r:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return ops.value / best
+
+
+def unpack_keys(k: np.ndarray):
+    k = np.asarray(k, np.uint32)
+    return (k >> np.uint32(IDX_BITS)).astype(np.int64), (k & np.uint32(IDX_MASK)).astype(np.int64), k >= np.uint32(0x80000000)

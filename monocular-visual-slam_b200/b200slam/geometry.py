@@ -1,0 +1,156 @@
+"""Host-side two-view geometry that follows the device kernels in the pose path.
+
+These are the steps of the reference that run ONCE per frame pair after the batched
+kernels have picked the winning hypothesis (SURVEY.md §8 a8 tail, a11, a12) — the refit
+on all inliers, the cheirality vote and the parallax statistics.  Vectorised NumPy
+(batched LAPACK), float64 like the reference.  They are next-row #2 candidates for a
+device kernel; they are not a fallback for anything that has one.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _homog(p: np.ndarray) -> np.ndarray:
+    return np.hstack([p, np.ones((len(p), 1))])
+
+
+def eight_point_refit(src: np.ndarray, dst: np.ndarray, K: np.ndarray) -> np.ndarray:
+    """n-point least-squares E on all inliers == the reference's final
+    ``eight_point_E(src[best_inliers], dst[best_inliers], K)`` (homography.py:344, :222-248),
+    ``K^T F K`` return included."""
+    n = len(src)
+    if n < 8:
+        raise ValueError("Eight correspondences required")
+    K = np.asarray(K, dtype=np.float64)
+    Kinv = np.linalg.inv(K)
+    a = (Kinv @ _homog(np.asarray(src)).T).T
+    b = (Kinv @ _homog(np.asarray(dst)).T).T
+    a = a / a[:, 2:3]
+    b = b / b[:, 2:3]
+    x, y, u, v = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+    A = np.stack([u * x, u * y, u, v * x, v * y, v, x, y, np.ones(n)], axis=1)
+    F = np.linalg.svd(A)[2][-1].reshape(3, 3)
+    U, S, Vt = np.linalg.svd(F)
+    S[2] = 0.0
+    return K.T @ (U @ np.diag(S) @ Vt) @ K
+
+
+def decompose_essential(E: np.ndarray, src: np.ndarray, dst: np.ndarray, K: np.ndarray):
+    """(R, t) with the most triangulated points in front of both cameras; first candidate
+    wins ties (homography.py:251-299).  The per-point 4x4 DLT SVDs of the reference's
+    Python double loop are issued as one batched SVD per candidate."""
+    E, K = np.asarray(E, dtype=np.float64), np.asarray(K, dtype=np.float64)
+    U, _, Vt = np.linalg.svd(E)
+    if np.linalg.det(U) < 0:
+        U = -U
+    if np.linalg.det(Vt) < 0:
+        Vt = -Vt
+    W = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    cands = [(U @ W @ Vt, U[:, 2]), (U @ W @ Vt, -U[:, 2]), (U @ W.T @ Vt, U[:, 2]), (U @ W.T @ Vt, -U[:, 2])]
+    s, d = np.asarray(src, dtype=np.float64), np.asarray(dst, dtype=np.float64)
+    P1 = K @ np.hstack([np.eye(3), np.zeros((3, 1))])
+    best, best_count = None, -1
+    for R, t in cands:
+        P2 = K @ np.hstack([R, t.reshape(3, 1)])
+        A = np.stack([s[:, 0:1] * P1[2] - P1[0], s[:, 1:2] * P1[2] - P1[1],
+                      d[:, 0:1] * P2[2] - P2[0], d[:, 1:2] * P2[2] - P2[1]], axis=1)      # (M,4,4)
+        if len(A):
+            X = np.linalg.svd(A)[2][:, -1, :]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                X3 = X[:, :3] / X[:, 3:4]
+                z2 = (X3 @ R.T + t)[:, 2]
+                count = int(np.sum((X3[:, 2] > 0) & (z2 > 0)))
+        else:
+            count = 0
+        if count > best_count:
+            best, best_count = (R, t), count
+    if best is None:
+        raise RuntimeError("Essential matrix decomposition failed")
+    return best
+
+
+# ---- homography branch (next-row #3: still host NumPy, batched) -------------------------
+
+def _normalise_batch(p: np.ndarray):
+    """Hartley normalisation per sample set; p: (H, n, 2) (homography.py:118-125)."""
+    c = p.mean(axis=1, keepdims=True)
+    rms = np.sqrt(((p - c) ** 2).sum(axis=2).mean(axis=1))
+    with np.errstate(divide="ignore"):
+        s = np.sqrt(2) / rms
+    T = np.zeros((len(p), 3, 3))
+    T[:, 0, 0] = s
+    T[:, 1, 1] = s
+    T[:, 0, 2] = -s * c[:, 0, 0]
+    T[:, 1, 2] = -s * c[:, 0, 1]
+    T[:, 2, 2] = 1.0
+    return (p - c) * s[:, None, None], T
+
+
+def dlt_homography_batch(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """Batched normalised DLT (homography.py:131-142); src, dst: (H, n, 2) -> (H, 3, 3)."""
+    sn, Ts = _normalise_batch(src)
+    dn, Td = _normalise_batch(dst)
+    x, y, u, v = sn[..., 0], sn[..., 1], dn[..., 0], dn[..., 1]
+    z, o = np.zeros_like(x), np.ones_like(x)
+    r1 = np.stack([-x, -y, -o, z, z, z, u * x, u * y, u], axis=-1)
+    r2 = np.stack([z, z, z, -x, -y, -o, v * x, v * y, v], axis=-1)
+    A = np.stack([r1, r2], axis=2).reshape(len(src), -1, 9)
+    A = np.nan_to_num(A, nan=0.0, posinf=0.0, neginf=0.0)
+    Hn = np.linalg.svd(A)[2][:, -1, :].reshape(-1, 3, 3)
+    with np.errstate(all="ignore"):
+        Hm = np.linalg.solve(Td, Hn @ Ts)
+        return Hm / Hm[:, 2:3, 2:3]
+
+
+def ransac_homography(src, dst, th: float = 3.0, max_iter: int = 2000, rng=None):
+    """Batched restatement of ransac_homography (homography.py:148-216): same sampling
+    call, symmetric transfer error, strict-improvement + 0.8 n early-exit selection,
+    refit on the winner's inliers."""
+    src, dst = np.asarray(src, dtype=np.float64), np.asarray(dst, dtype=np.float64)
+    n = len(src)
+    if n < 4:
+        raise ValueError("At least four correspondences are required")
+    if rng is None:
+        rng = np.random.default_rng()
+        samples = np.argsort(rng.random((max_iter, n)), axis=1)[:, :4]
+    else:
+        samples = np.stack([rng.choice(n, 4, replace=False) for _ in range(max_iter)])
+    src_h, dst_h = _homog(src), _homog(dst)
+    best_h, best_count, best_mask = -1, 0, None
+    for lo in range(0, max_iter, 256):
+        idx = samples[lo:lo + 256]
+        Hs = dlt_homography_batch(src[idx], dst[idx])
+        with np.errstate(all="ignore"):
+            pf = src_h @ Hs.transpose(0, 2, 1)
+            pf = pf[..., :2] / pf[..., 2:3]
+            Hinv = np.linalg.pinv(Hs)
+            pb = dst_h @ Hinv.transpose(0, 2, 1)
+            pb = pb[..., :2] / pb[..., 2:3]
+            err = np.linalg.norm(pf - dst, axis=2) + np.linalg.norm(pb - src, axis=2)
+            masks = err < th
+        counts = masks.sum(axis=1)
+        done = False
+        for k, c in enumerate(counts):
+            if c > best_count:
+                best_h, best_count, best_mask = lo + k, int(c), masks[k]
+                if c > 0.8 * n:
+                    done = True
+                    break
+        if done:
+            break
+    if best_mask is None or best_count < 4:
+        raise RuntimeError("RANSAC failed — too few inliers")
+    inl = np.flatnonzero(best_mask)
+    return dlt_homography_batch(src[inl][None], dst[inl][None])[0], inl
+
+
+def decompose_homography(H, K=np.eye(3)):
+    """homography.py:59-78."""
+    Kinv = np.linalg.inv(np.asarray(K, dtype=np.float64))
+    h1, h2, h3 = H[:, 0], H[:, 1], H[:, 2]
+    norm = np.linalg.norm(Kinv @ h1)
+    r1, r2, t = Kinv @ h1 / norm, Kinv @ h2 / norm, Kinv @ h3 / norm
+    R = np.stack([r1, r2, np.cross(r1, r2)], axis=1)
+    U, _, Vt = np.linalg.svd(R)
+    return U @ Vt, t

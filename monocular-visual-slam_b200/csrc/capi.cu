@@ -1,0 +1,148 @@
+// capi.cu — C-ABI glue of libb2s.so: errors, device info, variant dispatch, pipe microbenchmarks.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b2s {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return B2S_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int hamming_popc_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
+                        const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt,
+                        int max_nq, int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best,
+                        int t_split, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// ---- pipe microbenchmarks: 8 independent chains x 8 unrolled = 64 instructions / iteration ----
+template <int WHICH>
+__global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
+  uint32_t x[8];
+  double d[8];
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    x[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x;
+    d[k] = 1.0 + 1e-9 * (double)x[k];
+    f[k] = 1.0f + 1e-7f * (float)(x[k] & 1023);
+  }
+  const uint32_t c1 = blockIdx.x | 1u, c2 = threadIdx.x | 3u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (WHICH == 0) asm volatile("popc.b32 %0, %0;" : "+r"(x[k]));
+        if (WHICH == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(c1), "r"(c2));
+        if (WHICH == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(c1));
+        if (WHICH == 3) asm volatile("min.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(c2));
+        if (WHICH == 4) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[k]) : "d"(d[(k + 1) & 7]));
+        if (WHICH == 5) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(f[(k + 1) & 7]));
+        if (WHICH == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(c1), "r"(c2));
+      }
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc ^= x[k] ^ (uint32_t)__double_as_longlong(d[k]) ^ __float_as_uint(f[k]);
+  if (acc == 0x12345678u) sink[0] = acc;  // keeps the chains alive, practically never taken
+}
+
+}  // namespace b2s
+
+extern "C" {
+
+int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+
+const char* b2s_last_error(void) { return b2s::g_err; }
+
+int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm_count) {
+    B2S_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    *sm_count = v;
+  }
+  if (cc_major) {
+    B2S_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev));
+    *cc_major = v;
+  }
+  if (cc_minor) {
+    B2S_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev));
+    *cc_minor = v;
+  }
+  if (clock_khz) {
+    B2S_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev));
+    *clock_khz = v;
+  }
+  return B2S_OK;
+}
+
+int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const int32_t* q_off,
+                             const int32_t* t_off, const int32_t* q_src_row, const int32_t* t_src_row, int n_pairs,
+                             int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
+                             uint32_t* fwd_second, uint32_t* bwd_best, int variant, int t_split, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  using namespace b2s;
+  B2S_REQUIRE(n_pairs >= 0 && total_nq >= 0 && total_nt >= 0 && max_nq >= 0 && max_nt >= 0, "negative size");
+  B2S_REQUIRE(max_nq < B2S_MAX_ROWS_PER_PAIR && max_nt < B2S_MAX_ROWS_PER_PAIR,
+              "more than 2^22-1 rows in one pair does not fit the packed key");
+  if (n_pairs == 0) return B2S_OK;
+  B2S_REQUIRE(q_off && t_off && fwd_best && fwd_second && bwd_best, "null pointer");
+  B2S_REQUIRE((total_nq == 0 || q_desc) && (total_nt == 0 || t_desc), "null descriptor pointer");
+  B2S_REQUIRE((((uintptr_t)q_desc | (uintptr_t)t_desc) & 15u) == 0, "descriptor buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (variant == B2S_VARIANT_POPC) {
+    return hamming_popc_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt,
+                               max_nq, max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
+                               st);
+  }
+  set_error("Hamming variant %d is not built into this library", variant);
+  return B2S_ERR_UNSUPPORTED;
+}
+
+int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
+  using namespace b2s;
+  B2S_REQUIRE(which >= 0 && which <= 6, "which must be 0..6");
+  B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
+  const int grid = sm_count() * ctas_per_sm;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (which) {
+    case 0: pipe_kernel<0><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 1: pipe_kernel<1><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 2: pipe_kernel<2><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 3: pipe_kernel<3><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 4: pipe_kernel<4><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 5: pipe_kernel<5><<<grid, 256, 0, st>>>(iters, sink); break;
+    default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
+  }
+  B2S_CUDA(cudaGetLastError());
+  if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * 64.0;
+  return B2S_OK;
+}
+
+}  // extern "C"

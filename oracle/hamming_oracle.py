@@ -7,7 +7,7 @@ module (see oracle/__init__.py).
 
 Packed keys
 -----------
-``key = (distance << 23) | index`` (uint32, distance <= 256, index < 2**23).
+``key = (distance << 22) | index`` (uint32, distance <= 256, index < 2**22; any key >= 0x80000000 is "none").
 ``min`` over keys == the lexicographic ``(distance, index)`` minimum, which is
 OpenCV's tie rule (lowest train index wins a tie).
 ``NONE_KEY = 0xFFFFFFFF`` marks "no such neighbour" (e.g. second-best when the
@@ -20,7 +20,7 @@ import math
 
 import numpy as np
 
-IDX_BITS = 23
+IDX_BITS = 22
 IDX_MASK = (1 << IDX_BITS) - 1
 NONE_KEY = np.uint32(0xFFFFFFFF)
 
@@ -77,7 +77,7 @@ def packed_keys(q: np.ndarray, t: np.ndarray):
     D = hamming_matrix(q, t)
     nq, nt = D.shape
     if nq >= (1 << IDX_BITS) or nt >= (1 << IDX_BITS):
-        raise ValueError("too many rows for 23-bit indices")
+        raise ValueError("too many rows for 22-bit indices")
     kf = (D.astype(np.uint32) << IDX_BITS) | np.arange(nt, dtype=np.uint32)[None, :]
     kb = (D.astype(np.uint32) << IDX_BITS) | np.arange(nq, dtype=np.uint32)[:, None]
     if nt == 0:

@@ -1,0 +1,113 @@
+"""GPU drop-in tests: the reference-shaped interfaces (integration.*) behave like the
+reference's own — scenarios restated from /root/reference/tests/test_feature_pipeline.py,
+test_robust_pose_estimator.py, test_loop_closure_verification.py, test_keyframe_manager.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _project(P, R, t):
+    c = (R @ P.T).T + t
+    return (c[:, :2] / c[:, 2:3]).astype(np.float32)
+
+
+def _kps(p):
+    return [cv2.KeyPoint(float(x), float(y), 1.0) for x, y in p]
+
+
+def _matches(n):
+    return [cv2.DMatch(_queryIdx=i, _trainIdx=i, _distance=0.0) for i in range(n)]
+
+
+def test_pipeline_on_orb_images_equals_cv2(golden_dir):
+    from integration.feature_pipeline_bridge import (FeaturePipelineConfig, adaptive_ransac_threshold,
+                                                     build_feature_pipeline, matches_to_points)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 255, size=(240, 320), dtype=np.uint8)
+    b = np.roll(a, 3, axis=1)
+    for cross in (True, False):
+        cfg = FeaturePipelineConfig(name="orb", nfeatures=500, cross_check=cross)
+        pipe = build_feature_pipeline(cfg)
+        ka, da = pipe.detect_and_describe(a)
+        kb, db = pipe.detect_and_describe(b)
+        got = pipe.match(da, db)
+        assert isinstance(got, list)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=cross)
+        if cross:
+            want = list(bf.match(da, db))
+        else:
+            want = [p[0] for p in bf.knnMatch(da, db, k=2) if len(p) == 2 and p[0].distance < cfg.ratio_test * p[1].distance]
+        want.sort(key=lambda m: m.distance)
+        want = want[:cfg.max_matches]
+        assert [(m.queryIdx, m.trainIdx, m.distance, m.imgIdx) for m in got] == \
+               [(m.queryIdx, m.trainIdx, m.distance, m.imgIdx) for m in want]
+        pa, pb = matches_to_points(ka, kb, got)
+        th = adaptive_ransac_threshold(pa, pb, 0.01, 0.005, 0.03)
+        assert 0.005 <= th <= 0.03
+        st = pipe.match_stats(got)
+        assert st.match_count == len(got)
+    assert pipe.match(None, db) == [] and pipe.match(da, np.zeros((0, 32), np.uint8)) == []
+
+
+def test_identical_descriptors_match_ratio_one():
+    """tests/test_keyframe_manager.py:30-37 — identical 50x32 descriptors all cross-match."""
+    from integration.pose_bridge import CrossCheckMatcher
+    d = np.random.default_rng(0).integers(0, 256, (50, 32), dtype=np.uint8)
+    ms = CrossCheckMatcher().match(d, d)
+    assert [(m.queryIdx, m.trainIdx, m.distance) for m in ms] == [(i, i, 0.0) for i in range(50)]
+
+
+def test_robust_pose_estimator_scenarios():
+    from integration.pose_bridge import PoseEstimationFailure, RobustPoseEstimator, RobustPoseEstimatorConfig
+    K = np.eye(3)
+
+    def scene(seed, n, t):
+        P = np.random.default_rng(seed).uniform(-1, 1, (n, 3)) + np.array([0, 0, 3.0])
+        return _kps(_project(P, np.eye(3), np.zeros(3))), _kps(_project(P, np.eye(3), np.array(t)))
+
+    k1, k2 = scene(0, 50, [0.1, 0, 0])
+    est = RobustPoseEstimator(RobustPoseEstimatorConfig(min_matches=20, min_parallax=0.0)).estimate_pose(k1, k2, _matches(50), K)
+    assert est.diagnostics.inliers > 0 and est.diagnostics.method in {"essential", "homography"}
+    assert abs(np.linalg.norm(est.translation) - 1.0) < 1e-9
+
+    k1, k2 = scene(1, 40, [0.01, 0, 0])
+    with pytest.raises(PoseEstimationFailure) as e:
+        RobustPoseEstimator(RobustPoseEstimatorConfig(min_matches=20, min_parallax=10.0)).estimate_pose(k1, k2, _matches(40), K)
+    assert e.value.reason == "low_parallax"
+
+    k1, k2 = scene(2, 50, [0.2, 0, 0])
+    with pytest.raises(PoseEstimationFailure) as e:
+        RobustPoseEstimator(RobustPoseEstimatorConfig(min_matches=20, min_cheirality_ratio=1.1, min_parallax=0.0)).estimate_pose(k1, k2, _matches(50), K)
+    assert e.value.reason == "cheirality_ratio"
+
+    with pytest.raises(ValueError):
+        RobustPoseEstimator(RobustPoseEstimatorConfig()).estimate_pose(k1, k2, _matches(5), K)
+
+
+def test_pose_from_orb_with_inliers_identity_intrinsics():
+    """tests/test_loop_closure_verification.py restated in the K = I regime (the reference's
+    own fx=500 variant fails on the reference because of its intrinsics quirk, SURVEY finding 3):
+    identical descriptor sets -> all 40 matched, >= 80 % inliers, pose recovered."""
+    from integration.pose_bridge import estimate_pose_from_orb_with_inliers
+    rng = np.random.default_rng(42)
+    P = rng.uniform(-1, 1, (40, 3))
+    P[:, 2] += 4.0
+    yaw = 0.05
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    t = np.array([0.2, 0.0, 0.0])
+    desc = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    Re, te, inl, mc = estimate_pose_from_orb_with_inliers(_kps(_project(P, np.eye(3), np.zeros(3))), desc,
+                                                          _kps(_project(P, R, t)), desc, np.eye(3),
+                                                          ransac_threshold=0.01, min_matches=20)
+    assert mc == 40 and len(inl) >= 32
+    assert Re.shape == (3, 3) and te.shape == (3,)
+    np.testing.assert_allclose(Re, R, atol=1e-3)
+    np.testing.assert_allclose(te / np.linalg.norm(te), t / np.linalg.norm(t), atol=1e-2)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()

@@ -1,0 +1,40 @@
+"""CPU, build container only: the reference's own modules import through the
+``integration`` package this repo provides (the shim at /root/reference/feature_pipeline.py:1
+is dangling without it), and the reference tests that do not need a device pass unmodified.
+Skipped where /root/reference does not exist (the GPU box)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+REF = Path("/root/reference")
+ROOT = Path(__file__).resolve().parents[1]
+
+pytestmark = pytest.mark.skipif(not REF.exists(), reason="reference tree not present")
+
+
+def _run(code: str, timeout=300):
+    env = dict(os.environ, PYTHONPATH=f"{ROOT}{os.pathsep}{REF}", PYTHONDONTWRITEBYTECODE="1")
+    return subprocess.run([sys.executable, "-c", code], cwd="/tmp", env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_shim_resolves_and_importers_load():
+    r = _run("import feature_pipeline, robust_pose_estimator, slam_api, feature_control_plane;"
+             "import integration.feature_pipeline_bridge as b;"
+             "assert feature_pipeline.FeaturePipelineConfig is b.FeaturePipelineConfig;"
+             "from integration.pose_bridge import install; p = install(); print(sorted(p))")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "homography.ransac_essential" in r.stdout and "persistent_map._build_matcher" in r.stdout
+
+
+@pytest.mark.parametrize("test_file", ["test_slam_api.py", "test_feature_control_plane.py", "test_tracking_control_plane.py"])
+def test_reference_tests_pass_with_the_bridge(test_file, tmp_path):
+    env = dict(os.environ, PYTHONPATH=f"{ROOT}{os.pathsep}{REF}", PYTHONDONTWRITEBYTECODE="1")
+    for attempt in range(3):        # the reference's control-plane tests are timing-sensitive on a loaded box
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(REF / "tests" / test_file),
+                            "--rootdir", str(tmp_path)], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+        if r.returncode == 0:
+            break
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
