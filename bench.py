@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — frame-pairs/s of the ORB front-end hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One *step* = one pass of the whole hot path over one batch of synthetic frame pairs:
+Hamming kNN-2 (+ratio LUT + cross-check + top-500 select) on 2000x2000 ORB descriptors,
+then 2000 8-point essential-matrix hypotheses per pair solved on device, float64 Sampson
+scoring against the selected correspondences, winner + inlier mask.
+Workload = BASELINE.json configs[1] (KITTI-shaped synthetic sequence, consecutive-pair
+tracking, 2000 descriptors / frame).  Weak scaling: every rank owns its own batch; for
+N > 1 each step ends with the path's only collective, an NCCL all-gather of per-pair
+result records.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "monocular-visual-slam_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "frame-pairs/sec (2k ORB kNN+ratio+RANSAC E)"
+UNIT = "frame-pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=296, help="frame pairs per GPU per step (2 per SM)")
+    ap.add_argument("--nfeat", type=int, default=2000)
+    ap.add_argument("--hyps", type=int, default=2000)
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="CPU baseline sample size (0 = one per core, min 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="i8", choices=["popc", "i8"], help="Hamming kernel: K1 POPC or K2 tcgen05 kind::i8")
+    ap.add_argument("--sweep", action="store_true", help="also time every POPC-kernel configuration (extra key)")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": "BASELINE configs[1]: KITTI-shaped synthetic 1241x376 sequence, consecutive-pair tracking, "
+                        f"{a.nfeat} ORB descriptors/frame, kNN-2 + ratio 0.8 + cross-check + top-500, "
+                        f"{a.hyps} 8-point E hypotheses/pair, float64 Sampson th=0.01",
+            "pairs_per_gpu_per_step": a.pairs, "descriptors_per_frame": a.nfeat, "hypotheses": a.hyps,
+            "max_matches": 500, "parallelism": f"pair-sharded x{world}",
+            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)"}
+
+
+# ------------------------------------------------------------------------------------ #
+# CPU arm (reference path port; see oracle/reference_path.py)
+# ------------------------------------------------------------------------------------ #
+
+def cpu_arm(a, n_pairs, steps=1, warmup=0):
+    from b200slam.synthetic import tracking_pairs
+    from oracle import reference_path as rp
+
+    cores = os.cpu_count() or 1
+    n_pairs = n_pairs or max(8, cores)
+    qs, ts, kq, kt = tracking_pairs(n_pairs, a.nfeat, seed=1234)
+    pairs = list(zip(qs, ts, kq, kt))
+    for _ in range(warmup):
+        rp.run_pairs(pairs[: max(1, min(len(pairs), cores))], workers=cores, max_iter=a.hyps)
+    times, res = [], None
+    for _ in range(steps):
+        res, sec, workers = rp.run_pairs(pairs, workers=cores, max_iter=a.hyps)
+        times.append(sec)
+    sec = float(np.mean(times))
+    # same work as the GPU unit (every hypothesis scored) on a smaller sample
+    nfull = max(1, min(len(pairs), cores))
+    _, sec_full, _ = rp.run_pairs(pairs[:nfull], workers=cores, max_iter=a.hyps, full_budget=True)
+    return {"value": n_pairs / sec, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": f"{n_pairs} pairs/step x {steps} step(s), one process per core, cv2.BFMatcher knnMatch+crossCheck "
+                      f"(1 thread each) + the reference's Python RANSAC loop with its early exit (8-point SVD + NumPy Sampson "
+                      f"per iteration, max_iter={a.hyps})",
+            "value_full_budget": nfull / sec_full,
+            "sample_full_budget": f"{nfull} pairs, all {a.hyps} hypotheses scored (no early exit) = the GPU unit's work",
+            "mean_matches": float(np.mean([r[0] for r in res])), "sec_per_step": sec}
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_arm(a, a.cpu_pairs, steps=max(1, a.steps), warmup=min(a.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 popcount + f64 Sampson", "data": "synthetic",
+            "config": workload_config(a, 1), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ #
+# clocks sampler
+# ------------------------------------------------------------------------------------ #
+
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ #
+# B200 arm
+# ------------------------------------------------------------------------------------ #
+
+def b200_main(a):
+    import torch
+    import torch.distributed as dist
+
+    from b200slam import _capi
+    from b200slam.frontend import Frontend, FrontendConfig, PairBatch, pipe_microbench
+    from b200slam.synthetic import tracking_pairs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = _capi.load_library()
+
+    # ---- synthetic batch: generate a few distinct pairs on the host, tile to the batch size ----
+    base = min(a.pairs, 16)
+    qs, ts, kq, kt = tracking_pairs(base, a.nfeat, seed=1234 + rank)
+    reps = (a.pairs + base - 1) // base
+    qs, ts, kq, kt = [(x * reps)[: a.pairs] for x in (qs, ts, kq, kt)]
+    cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337 + rank)
+    variant = _capi.VARIANT_I8MMA if a.variant == "i8" else _capi.VARIANT_POPC
+    fe = Frontend(cfg, variant=variant)
+    batch = PairBatch.from_host(qs, ts, kq, kt, device=dev)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pair_ids = torch.arange(rank * a.pairs, (rank + 1) * a.pairs, dtype=torch.int32, device=dev)
+
+    def step():
+        res = fe.run(batch)
+        if world > 1:
+            rec = torch.stack([res.sel.count, res.best_h, res.best_count, pair_ids], dim=1).contiguous()
+            _allgather(rec)
+        return res
+
+    gather_buf = torch.empty((world * a.pairs, 4), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def _allgather(rec):
+        dist.all_gather_into_tensor(gather_buf, rec)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            flush.fill_(0)                      # evict L2 between timed steps (outside the event pair)
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in ev]
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.b2s_launch_count()
+    ms = timed(step, a.steps, a.warmup)
+    launches = int(lib.b2s_launch_count() - l0)
+    warm_launches_per_step = launches // (a.steps + a.warmup)
+    total_ms = float(np.sum(ms))
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = world * a.pairs * a.steps / (total_ms * 1e-3)
+
+    # ---- dominant kernel alone: Hamming kNN-2 (CUDA events on the launching stream) ----
+    def k1():
+        fe.matcher.knn2(batch)
+    k1_ms = timed(k1, a.steps, a.warmup)
+    k1_avg = float(np.mean(k1_ms)) * 1e-3
+    # the other variant, for the K1-vs-K2 decision record
+    from b200slam.frontend import HammingMatcher
+    other = HammingMatcher(variant=_capi.VARIANT_POPC if a.variant == "i8" else _capi.VARIANT_I8MMA)
+    other_avg = float(np.mean(timed(lambda: other.knn2(batch), max(3, a.steps // 2), 2))) * 1e-3
+    variants_ms = {a.variant: k1_avg * 1e3, ("popc" if a.variant == "i8" else "i8"): other_avg * 1e3}
+    popc_ops = 8.0 * sum(len(q) * len(t) for q, t in zip(qs, ts))          # algorithmic POPC32 per launch
+    alg_bytes = float(batch.total_nq + batch.total_nt) * 32 + 4.0 * (2 * batch.total_nq + batch.total_nt)
+
+    # ---- end to end through host buffers (pinned host -> device -> kernels -> host) ----
+    host = HostStage(batch, qs, ts, kq, kt, torch, dev)
+
+    def e2e_step():
+        host.upload()
+        res = fe.run(host.batch)
+        host.download(res)
+        if world > 1:
+            rec = torch.stack([res.sel.count, res.best_h, res.best_count, pair_ids], dim=1).contiguous()
+            _allgather(rec)
+        torch.cuda.current_stream().synchronize()
+    e2e_ms = timed(e2e_step, a.steps, a.warmup)
+    e2e_total = float(np.sum(e2e_ms))
+    if world > 1:
+        tt = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_total = float(tt.item())
+    e2e_value = world * a.pairs * a.steps / (e2e_total * 1e-3)
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline denominators measured live ----
+    peaks = {}
+    mp_path = ROOT / "MEASURED_PEAKS.json"
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if mp_path.exists():
+        hbm_peak, hbm_src = float(json.loads(mp_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json"
+    for name in ("popc", "lop3", "imnmx", "imad", "dfma"):
+        peaks[name] = pipe_microbench(name)
+    sms, _, _, clock_khz = _devinfo(lib)
+    popc_peak = peaks["popc"]
+    achieved = popc_ops / k1_avg
+    bf16_peak = float(json.loads(mp_path.read_text()).get("bf16_tflops", 1590.0)) if mp_path.exists() else 1590.0
+    i8_ops = 64.0 * popc_ops                                   # 2*256 int8 ops per descriptor pair = 64 per POPC32
+    roof_tensor = {"bound": "tensor", "achieved": i8_ops / (variants_ms["i8"] * 1e-3) / 1e12, "peak": 2.0 * bf16_peak,
+                   "unit": "TOP/s (int8)", "frac": i8_ops / (variants_ms["i8"] * 1e-3) / 1e12 / (2.0 * bf16_peak),
+                   "traffic": None, "kernel": "hamming_knn2_i8_kernel (+2 expand_pm1 launches)", "kernel_ms": variants_ms["i8"],
+                   "peak_source": "2 x measured cuBLAS bf16 (%s): no int8 GEMM peak is measured on this pool" % hbm_src,
+                   "note": "algorithmic = ONE 2*256*Nq*Nt contraction per pair; the kernel issues two (D and D^T) so that the "
+                           "column minimum is a per-thread reduction, so 0.5 is its structural ceiling"}
+    roof = {"bound": "int-popc-pipe", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
+            "frac": achieved / popc_peak, "traffic": None, "kernel": "hamming_knn2_%s_kernel" % a.variant,
+            "kernel_ms": k1_avg * 1e3, "algorithmic_popc_per_launch": popc_ops, "tensor_view": roof_tensor,
+            "hamming_variants_ms": variants_ms,
+            "peak_source": "b2s_pipe_microbench(popc) measured in this run: %.1f POPC/clk/SM at %d MHz max clock" % (
+                popc_peak / sms / (clock_khz * 1e3), clock_khz // 1000),
+            "hbm": {"bound": "hbm", "achieved": alg_bytes / k1_avg / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / k1_avg / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "note": "not the binding roofline: 210 POPC per byte (SURVEY 8d)"},
+            "pipe_rates_per_clk_per_sm": {k: v / sms / (clock_khz * 1e3) for k, v in peaks.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 popcount + f64 Sampson", "data": "synthetic", "config": workload_config(a, world),
+            "clocks": clk, "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+                    "ms_per_step": e2e_total / a.steps},
+            "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
+            "kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
+    if a.sweep:
+        line["popc_kernel_sweep_ms"] = sweep(lib, fe, batch, timed, a)
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_arm(a, a.cpu_pairs)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _devinfo(lib):
+    import ctypes as C
+    v = [C.c_int(0) for _ in range(4)]
+    lib.b2s_device_info(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def _getcfg(lib):
+    import ctypes as C
+    v = [C.c_int(0) for _ in range(3)]
+    lib.b2s_hamming_get_config(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def sweep(lib, fe, batch, timed, a):
+    out = {}
+    keep = _getcfg(lib)
+    for rows in (2, 4):
+        for warps in (4, 8):
+            for csa in (0, 1, 2, 3):
+                lib.b2s_hamming_set_config(csa, rows, warps)
+                out[f"csa{csa}_r{rows}_w{warps}"] = float(np.mean(timed(lambda: fe.matcher.knn2(batch), 5, 2)))
+    lib.b2s_hamming_set_config(*keep)
+    return out
+
+
+class HostStage:
+    """Pinned host staging for the end-to-end number: descriptors + keypoints go up every
+    step; match triplets, counts, winners and inlier masks come back every step."""
+
+    def __init__(self, batch, qs, ts, kq, kt, torch, dev):
+        import copy
+        self.torch = torch
+        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        self.h = {"q": pin(np.concatenate(qs)), "t": pin(np.concatenate(ts)), "kq": pin(np.concatenate(kq)), "kt": pin(np.concatenate(kt))}
+        self.batch = copy.copy(batch)
+        self.batch.q_desc = torch.empty_like(batch.q_desc)
+        self.batch.t_desc = torch.empty_like(batch.t_desc)
+        self.batch.kp_q = torch.empty_like(batch.kp_q)
+        self.batch.kp_t = torch.empty_like(batch.kp_t)
+        n, nq = batch.n_pairs, batch.total_nq
+        self.o = {"count": torch.empty(n, dtype=torch.int32).pin_memory(), "best_h": torch.empty(n, dtype=torch.int32).pin_memory(),
+                  "best_count": torch.empty(n, dtype=torch.int32).pin_memory(),
+                  "out_q": torch.empty(nq, dtype=torch.int32).pin_memory(), "out_t": torch.empty(nq, dtype=torch.int32).pin_memory(),
+                  "out_d": torch.empty(nq, dtype=torch.int32).pin_memory(), "mask": torch.empty(nq, dtype=torch.uint8).pin_memory()}
+        self.h2d_bytes = int(sum(v.numel() * v.element_size() for v in self.h.values()))
+        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.o.values()))
+
+    def upload(self):
+        b = self.batch
+        b.q_desc.copy_(self.h["q"], non_blocking=True)
+        b.t_desc.copy_(self.h["t"], non_blocking=True)
+        b.kp_q.copy_(self.h["kq"], non_blocking=True)
+        b.kp_t.copy_(self.h["kt"], non_blocking=True)
+
+    def download(self, res):
+        o = self.o
+        o["count"].copy_(res.sel.count, non_blocking=True)
+        o["best_h"].copy_(res.best_h, non_blocking=True)
+        o["best_count"].copy_(res.best_count, non_blocking=True)
+        o["out_q"].copy_(res.sel.out_q, non_blocking=True)
+        o["out_t"].copy_(res.sel.out_t, non_blocking=True)
+        o["out_d"].copy_(res.sel.out_d, non_blocking=True)
+        o["mask"].copy_(res.inlier_mask, non_blocking=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        b200_main(a)
+
+
+if __name__ == "__main__":
+    main()

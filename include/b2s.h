@@ -46,6 +46,8 @@ extern "C" {
 #define B2S_VARIANT_I8MMA 1 /* tcgen05.mma kind::i8 +-1 contraction (K2) */
 
 int b2s_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py gpu_launches). */
+unsigned long long b2s_launch_count(void);
 const char* b2s_last_error(void);
 /* sm_count / cc_major / cc_minor / sm clock kHz of the current device. */
 int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
@@ -67,6 +69,11 @@ int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz)
  * train axis (0 = choose automatically); workspace must hold
  * b2s_hamming_workspace_bytes(total_nq, t_split_max) bytes when t_split != 1. */
 size_t b2s_hamming_workspace_bytes(int total_nq, int t_split);
+/* Workspace of either variant.  The I8MMA variant stages every descriptor as 256 int8
+ * (+1/-1) in 32 KB operand tiles: n_pairs * (ceil(max_nq/128) + ceil(max_nt/128)) * 32 KB,
+ * 128-byte aligned; t_split is ignored by it. */
+size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt,
+                                     int t_split);
 int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc,
                              const int32_t* q_off, const int32_t* t_off,
                              const int32_t* q_src_row, const int32_t* t_src_row, int n_pairs,

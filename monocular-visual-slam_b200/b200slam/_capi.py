@@ -40,12 +40,16 @@ def _declare(lib):
     ip = C.POINTER(C.c_int)
     lib.b2s_abi_version.restype = i32
     lib.b2s_abi_version.argtypes = []
+    lib.b2s_launch_count.restype = C.c_ulonglong
+    lib.b2s_launch_count.argtypes = []
     lib.b2s_last_error.restype = C.c_char_p
     lib.b2s_last_error.argtypes = []
     lib.b2s_device_info.restype = i32
     lib.b2s_device_info.argtypes = [ip, ip, ip, ip]
     lib.b2s_hamming_workspace_bytes.restype = sz
     lib.b2s_hamming_workspace_bytes.argtypes = [i32, i32]
+    lib.b2s_hamming_workspace_bytes_v.restype = sz
+    lib.b2s_hamming_workspace_bytes_v.argtypes = [i32, i32, i32, i32, i32, i32]
     lib.b2s_hamming_knn2_batched.restype = i32
     lib.b2s_hamming_knn2_batched.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                              vp, vp, vp, i32, i32, vp, sz, vp]
@@ -68,7 +72,7 @@ def _declare(lib):
 
 
 EXPORTS = (
-    "b2s_abi_version", "b2s_last_error", "b2s_device_info", "b2s_hamming_workspace_bytes",
+    "b2s_abi_version", "b2s_launch_count", "b2s_last_error", "b2s_device_info", "b2s_hamming_workspace_bytes", "b2s_hamming_workspace_bytes_v",
     "b2s_hamming_knn2_batched", "b2s_hamming_set_config", "b2s_hamming_get_config",
     "b2s_select_matches", "b2s_eight_point_batched", "b2s_ransac_score_batched",
     "b2s_ransac_select", "b2s_pipe_microbench",

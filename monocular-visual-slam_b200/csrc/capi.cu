@@ -7,6 +7,9 @@
 namespace b2s {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void note_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -36,6 +39,12 @@ int hamming_popc_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off
                         const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt,
                         int max_nq, int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best,
                         int t_split, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt);
+int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
+                      const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
+                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st);
 
 // ---- pipe microbenchmarks: 8 independent chains x 8 unrolled = 64 instructions / iteration ----
 template <int WHICH>
@@ -76,6 +85,8 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
 extern "C" {
 
 int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+
+unsigned long long b2s_launch_count(void) { return __atomic_load_n(&b2s::g_launches, __ATOMIC_RELAXED); }
 
 const char* b2s_last_error(void) { return b2s::g_err; }
 
@@ -121,8 +132,17 @@ int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const
                                max_nq, max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
                                st);
   }
+  if (variant == B2S_VARIANT_I8MMA) {
+    return hamming_i8_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt, max_nq,
+                             max_nt, fwd_best, fwd_second, bwd_best, workspace, workspace_bytes, st);
+  }
   set_error("Hamming variant %d is not built into this library", variant);
   return B2S_ERR_UNSUPPORTED;
+}
+
+size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
+  if (variant == B2S_VARIANT_I8MMA) return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
+  return b2s_hamming_workspace_bytes(total_nq, t_split);
 }
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
@@ -141,6 +161,7 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }
   B2S_CUDA(cudaGetLastError());
+  note_launch();
   if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * 64.0;
   return B2S_OK;
 }

@@ -32,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+void note_launch(int n = 1);  // counts kernels launched by this library (b2s_launch_count)
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kIdxBits = B2S_IDX_BITS;

@@ -1,0 +1,368 @@
+// hamming_i8.cu — K2: Hamming kNN-2 + column minimum on the 5th-gen tensor cores.
+//
+// Same contract as K1 (hamming_popc.cu); replaces the same reference calls
+// (/root/reference/feature_pipeline.py.bak:68,82,84; homography.py:12-15,21-23).
+//
+// Hamming as a dense contraction: map bit b -> 1 - 2b (int8 +-1); then for two 256-bit
+// descriptors  dot = 256 - 2*ham, so  key = ham<<22 | idx = dot * (-2^21) + (2^29 + idx)
+// exactly (dot is even).  tcgen05.mma kind::i8 (M=128, N=128, K=32 per instruction, int32
+// accumulators in TMEM) produces a 128x128 tile of dots in 8 instructions.
+//
+// Two products per tile pair so that BOTH reductions are per-thread (a TMEM lane is a
+// matrix row and each epilogue thread owns one lane):
+//     D1 = Qtile . Ttile^T   lanes = queries,  columns = train rows  -> per-row top-2
+//     D2 = Ttile . Qtile^T   lanes = train rows, columns = queries   -> per-column minimum
+// Both read the same two shared-memory tiles (K-major, canonical no-swizzle core-matrix
+// layout), only the A/B descriptor roles swap.
+//
+// Pipeline (one CTA = one (pair, 128-query tile), 320 threads):
+//   warp 0   producer : cp.async.bulk (TMA engine) of pre-expanded 32 KB operand tiles into
+//                       a 4-stage ring, mbarrier expect_tx / complete_tx
+//   warp 1   MMA      : one thread issues 16 tcgen05.mma per train tile, tcgen05.commit
+//                       releases the smem stage and publishes the TMEM accumulator stage
+//   warps 2-9 epilogue: tcgen05.ld 32x32b.x32 (thread = TMEM lane), IMAD to a packed key,
+//                       4-way interleaved top-2 / min chains, merge, atomicMin for columns
+// TMEM: 2 accumulator stages x (D1 128 cols + D2 128 cols) = 512 columns.
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int kI8Tile = 128;                 // rows per operand tile
+constexpr int kI8TileBytes = kI8Tile * 256;  // 32 KB of +-1 int8
+constexpr int kI8Stages = 4;
+constexpr int kI8Threads = 320;
+constexpr uint32_t kKeyScale = 1u << 21;     // key = dot * (-2^21) + 2^29 + idx
+constexpr uint32_t kKeyBias = 1u << 29;
+
+// ---- pre-pass: 256 bits -> 256 int8 (+1 / -1) in the UMMA canonical K-major layout ------
+// Tile = 128 rows x 256 bytes.  16-byte unit (row r, k-chunk kc) sits at unit index
+// kc*128 + r: 8 rows x 16 B form one 128-byte core matrix, core matrices of 8-row groups
+// are 128 B apart (SBO), the 16 k-chunks are 2048 B apart (LBO).
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {
+  // bit i of nib -> byte i: 0x01 for a clear bit (+1), 0xFF for a set bit (-1)
+  return (((nib * 0x00204081u) & 0x01010101u) * 0xFEu) | 0x01010101u;
+}
+
+__global__ void __launch_bounds__(256) expand_pm1_kernel(const uint8_t* __restrict__ desc,
+                                                         const int32_t* __restrict__ off,
+                                                         const int32_t* __restrict__ src, int tiles_per_pair,
+                                                         uint4* __restrict__ out) {
+  const int pair = blockIdx.y;
+  const int o = off[pair];
+  const int n = off[pair + 1] - o;
+  const int in0 = src ? src[pair] : o;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte unit within the pair's tiles
+  const int tile = u >> 11, w = u & 2047;
+  if (tile >= tiles_per_pair) return;
+  if (tile * kI8Tile >= n) return;  // tile never read
+  const int kc = w >> 7, r = w & 127;
+  const int row = tile * kI8Tile + r;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < n) {
+    const uint32_t bits = *reinterpret_cast<const uint16_t*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES + 2 * kc);
+    v.x = spread4(bits & 15u);
+    v.y = spread4((bits >> 4) & 15u);
+    v.z = spread4((bits >> 8) & 15u);
+    v.w = spread4((bits >> 12) & 15u);
+  }
+  out[((size_t)pair * tiles_per_pair + tile) * 2048 + w] = v;
+}
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends in hardware for a bounded time; a broken pipeline traps instead of hanging
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, LBO = 2048 B, SBO = 128 B, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)(2048u >> 4) << 16;         // leading (K-direction) byte offset, bits [16,30)
+  d |= (uint64_t)(128u >> 4) << 32;          // stride (8-row group) byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  return d;                                  // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: S32 accumulate, signed 8-bit A and B, both K-major, M = 128, N = 128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+#define TMEM_LD_X32(taddr, v)                                                                              \
+  asm volatile(                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
+      : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct I8Params {
+  const uint8_t* __restrict__ qx;  // expanded query tiles  [pair][q_tiles][32 KB]
+  const uint8_t* __restrict__ tx;  // expanded train tiles  [pair][t_tiles][32 KB]
+  const int32_t* __restrict__ q_off;
+  const int32_t* __restrict__ t_off;
+  uint32_t* __restrict__ fwd_best;
+  uint32_t* __restrict__ fwd_second;
+  uint32_t* __restrict__ bwd_best;
+  int q_tiles, t_tiles;
+};
+
+// keys of 32 accumulator columns (local column index c0 + k) folded into 4 interleaved
+// top-2 chains (ILP 4; a single chain would serialise on the 4-cycle ALU latency)
+template <bool TAIL>
+__device__ __forceinline__ void fold_top2(const uint32_t (&v)[32], int c0, int valid, uint32_t (&b)[4],
+                                          uint32_t (&s)[4]) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    uint32_t key = v[k] * (0u - kKeyScale) + (kKeyBias + (uint32_t)(c0 + k));
+    if (TAIL) key = (c0 + k < valid) ? key : kNone;
+    top2_insert(b[k & 3], s[k & 3], key);
+  }
+}
+template <bool TAIL>
+__device__ __forceinline__ void fold_min(const uint32_t (&v)[32], int c0, int valid, uint32_t (&m)[4]) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    uint32_t key = v[k] * (0u - kKeyScale) + (kKeyBias + (uint32_t)(c0 + k));
+    if (TAIL) key = (c0 + k < valid) ? key : kNone;
+    m[k & 3] = min(m[k & 3], key);
+  }
+}
+
+__global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_q = smem;                           // 32 KB
+  uint8_t* s_t = smem + kI8TileBytes;            // kI8Stages x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kI8Stages) * kI8TileBytes);
+  uint64_t* b_full = bars;                       // [kI8Stages]
+  uint64_t* b_empty = bars + kI8Stages;          // [kI8Stages]
+  uint64_t* b_tfull = bars + 2 * kI8Stages;      // [2]
+  uint64_t* b_tempty = bars + 2 * kI8Stages + 2; // [2]
+  uint64_t* b_q = bars + 2 * kI8Stages + 4;      // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kI8Stages + 5);
+  uint2* s_merge = reinterpret_cast<uint2*>(bars + 2 * kI8Stages + 6);  // [128] fwd halves meet here
+
+  const int pair = blockIdx.y, qt = blockIdx.x;
+  const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
+  const int q0 = qt * kI8Tile;
+  if (q0 >= nq) return;  // CTA-uniform
+  const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
+  const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kI8Stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&b_tfull[a], 1);
+      mbar_init(&b_tempty[a], 8);  // one elected arrive per epilogue warp
+    }
+    mbar_init(b_q, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM by shared-memory footprint)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      const uint8_t* qsrc = p.qx + ((size_t)pair * p.q_tiles + qt) * kI8TileBytes;
+      mbar_arrive_expect_tx(b_q, kI8TileBytes);
+      bulk_g2s(s_q, qsrc, kI8TileBytes, b_q);
+      const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
+      for (int t = 0; t < n_tt; ++t) {
+        const int s = t % kI8Stages;
+        if (t >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((uint32_t)(t / kI8Stages) - 1u) & 1u);
+        mbar_arrive_expect_tx(&b_full[s], kI8TileBytes);
+        bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, &b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait_bounded(b_q, 0);
+      const uint64_t qdesc = make_smem_desc(smem_u32(s_q));
+      for (int t = 0; t < n_tt; ++t) {
+        const int s = t % kI8Stages, a = t & 1;
+        if (t >= 2) mbar_wait_bounded(&b_tempty[a], ((uint32_t)(t >> 1) - 1u) & 1u);
+        mbar_wait_bounded(&b_full[s], (uint32_t)(t / kI8Stages) & 1u);
+        tc_fence_after();
+        const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
+        const uint32_t d1 = tmem_base + (uint32_t)a * 256u, d2 = d1 + 128u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // K = 32 bytes per instruction = two k-chunks = 4096 B apart (>>4 = 256)
+          tc_mma_i8(d1, qdesc + (uint64_t)k * 256u, tdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          tc_mma_i8(d2, tdesc + (uint64_t)k * 256u, qdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+        tc_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
+        tc_commit(&b_tfull[a]);  // accumulators complete
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp%4 = TMEM lane quarter, (warp-2)/4 = column half =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;  // TMEM lane = tile row
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int nq_valid = min(kI8Tile, nq - q0);
+    uint32_t gbest = kNone, gsecond = kNone;
+    for (int t = 0; t < n_tt; ++t) {
+      const int a = t & 1;
+      const int tbase = t * kI8Tile;
+      const int nt_valid = min(kI8Tile, nt - tbase);
+      mbar_wait_bounded(&b_tfull[a], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      // ---- D1: this thread's query row vs 64 train columns ----
+      const uint32_t c1 = lane_addr + (uint32_t)a * 256u + (uint32_t)half * 64u;
+      TMEM_LD_X32(c1, v0);
+      TMEM_LD_X32(c1 + 32u, v1);
+      tmem_ld_wait();
+      uint32_t b[4] = {kNone, kNone, kNone, kNone}, s2[4] = {kNone, kNone, kNone, kNone};
+      if (nt_valid == kI8Tile) {
+        fold_top2<false>(v0, half * 64, kI8Tile, b, s2);
+        fold_top2<false>(v1, half * 64 + 32, kI8Tile, b, s2);
+      } else {
+        fold_top2<true>(v0, half * 64, nt_valid, b, s2);
+        fold_top2<true>(v1, half * 64 + 32, nt_valid, b, s2);
+      }
+      // ---- D2: this thread's train row vs 64 query columns ----
+      const uint32_t c2 = c1 + 128u;
+      TMEM_LD_X32(c2, v0);
+      TMEM_LD_X32(c2 + 32u, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_tempty[a]);  // accumulator stage drained into registers
+      uint32_t m[4] = {kNone, kNone, kNone, kNone};
+      if (nq_valid == kI8Tile) {
+        fold_min<false>(v0, half * 64, kI8Tile, m);
+        fold_min<false>(v1, half * 64 + 32, kI8Tile, m);
+      } else {
+        fold_min<true>(v0, half * 64, nq_valid, m);
+        fold_min<true>(v1, half * 64 + 32, nq_valid, m);
+      }
+      // merge the 4 chains, rebase local indices to pair-local ones
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (b[k] != kNone) top2_insert(gbest, gsecond, b[k] + (uint32_t)tbase);
+        if (s2[k] != kNone) top2_insert(gbest, gsecond, s2[k] + (uint32_t)tbase);
+      }
+      const uint32_t cm = min(min(m[0], m[1]), min(m[2], m[3]));
+      if (row < nt_valid && cm != kNone) atomicMin(&p.bwd_best[to + tbase + row], cm + (uint32_t)q0);
+    }
+    // the two column halves of a query row meet in shared memory
+    if (half == 1) s_merge[row] = make_uint2(gbest, gsecond);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+    if (half == 0 && row < nq_valid) {
+      const uint2 o = s_merge[row];
+      top2_insert(gbest, gsecond, o.x);
+      top2_insert(gbest, gsecond, o.y);
+      p.fwd_best[qo + q0 + row] = gbest;
+      p.fwd_second[qo + q0 + row] = gsecond;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+constexpr size_t kI8SmemBytes = (size_t)(1 + kI8Stages) * kI8TileBytes + 8 * (2 * kI8Stages + 6) + 128 * sizeof(uint2);
+
+size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
+  const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
+  return (size_t)n_pairs * (qt + tt) * kI8TileBytes;
+}
+
+int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
+                      const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
+                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
+  B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
+  if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
+  if (total_nq > 0) {  // rows of pairs without train descriptors keep "none"
+    B2S_CUDA(cudaMemsetAsync(fwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+    B2S_CUDA(cudaMemsetAsync(fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+  }
+  if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0) return B2S_OK;
+  const int qt = (max_nq + kI8Tile - 1) / kI8Tile, tt = (max_nt + kI8Tile - 1) / kI8Tile;
+  const size_t need = hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
+  B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+              "i8 variant needs %zu workspace bytes (b2s_hamming_workspace_bytes_v), got %zu", need, workspace_bytes);
+  B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
+  uint8_t* qx = static_cast<uint8_t*>(workspace);
+  uint8_t* tx = qx + (size_t)n_pairs * qt * kI8TileBytes;
+  expand_pm1_kernel<<<dim3((qt * 2048 + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt,
+                                                                           reinterpret_cast<uint4*>(qx));
+  B2S_CUDA(cudaGetLastError());
+  expand_pm1_kernel<<<dim3((tt * 2048 + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt,
+                                                                           reinterpret_cast<uint4*>(tx));
+  B2S_CUDA(cudaGetLastError());
+  note_launch(2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kI8SmemBytes));
+    attr_set = true;
+  }
+  I8Params p;
+  p.qx = qx;
+  p.tx = tx;
+  p.q_off = q_off;
+  p.t_off = t_off;
+  p.fwd_best = fwd_best;
+  p.fwd_second = fwd_second;
+  p.bwd_best = bwd_best;
+  p.q_tiles = qt;
+  p.t_tiles = tt;
+  hamming_knn2_i8_kernel<<<dim3(qt, n_pairs), kI8Threads, kI8SmemBytes, st>>>(p);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
+
+}  // namespace b2s

@@ -38,16 +38,29 @@ struct HammingParams {
 constexpr int kTC = 128;    // train descriptors per chunk (4 KB)
 constexpr int kStages = 4;  // bulk-copy ring depth
 
+// Explicit LOP3s: NVVM otherwise pushes the XORs through the carry-save tree and emits
+// ~20 LOP3 per descriptor pair instead of 12-20 (measured: the 64-lane ALU pipe, not the
+// 16-lane POPC pipe, became the binder).  asm keeps the tree as written.
+__device__ __forceinline__ uint32_t xor2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, 0, 0x3c;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t and2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, 0, 0xc0;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ void csa(uint32_t& s, uint32_t& c, uint32_t a, uint32_t b, uint32_t d) {
-  s = a ^ b ^ d;                    // LOP3 0x96
-  c = (a & b) | (a & d) | (b & d);  // LOP3 0xE8
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(d));  // a ^ b ^ d
+  asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(c) : "r"(a), "r"(b), "r"(d));  // majority
 }
 
 // 256-bit Hamming distance.  LEVEL selects how many POPCs are traded for LOP3s.
 template <int LEVEL>
 __device__ __forceinline__ uint32_t ham256(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb) {
-  const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
-  const uint32_t x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
+  const uint32_t x0 = xor2(qa.x, ta.x), x1 = xor2(qa.y, ta.y), x2 = xor2(qa.z, ta.z), x3 = xor2(qa.w, ta.w);
+  const uint32_t x4 = xor2(qb.x, tb.x), x5 = xor2(qb.y, tb.y), x6 = xor2(qb.z, tb.z), x7 = xor2(qb.w, tb.w);
   if constexpr (LEVEL == 0) {
     return (__popc(x0) + __popc(x1) + __popc(x2)) + (__popc(x3) + __popc(x4) + __popc(x5)) +
            (__popc(x6) + __popc(x7));
@@ -55,15 +68,15 @@ __device__ __forceinline__ uint32_t ham256(const uint4& qa, const uint4& qb, con
     uint32_t s1, c1, s2, c2;
     csa(s1, c1, x0, x1, x2);
     csa(s2, c2, x3, x4, x5);
-    if constexpr (LEVEL == 1) {  // 6 POPC
+    if constexpr (LEVEL == 1) {  // 6 POPC, 12 LOP3
       return (__popc(s1) + __popc(s2) + __popc(x6)) + __popc(x7) + 2u * (__popc(c1) + __popc(c2));
     } else {
       uint32_t s3, c3;
       csa(s3, c3, s1, s2, x6);
-      if constexpr (LEVEL == 2) {  // 5 POPC
+      if constexpr (LEVEL == 2) {  // 5 POPC, 14 LOP3
         return (__popc(s3) + __popc(x7)) + 2u * (__popc(c1) + __popc(c2) + __popc(c3));
-      } else {  // 4 POPC
-        const uint32_t s4 = s3 ^ x7, c4 = s3 & x7;
+      } else {  // 4 POPC, 18 LOP3
+        const uint32_t s4 = xor2(s3, x7), c4 = and2(s3, x7);
         uint32_t s5, c5;
         csa(s5, c5, c1, c2, c3);
         return __popc(s4) + 2u * (__popc(s5) + __popc(c4)) + 4u * __popc(c5);
@@ -259,10 +272,12 @@ int hamming_popc_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off
   else if (R == 4 && W == 4) e = launch_rw<4, 4>(g_csa, grid, st, p);
   else e = launch_rw<4, 8>(g_csa, grid, st, p);
   B2S_CUDA(e);
+  note_launch();
   if (t_split > 1) {
     hamming_merge_kernel<<<(total_nq + 255) / 256, 256, 0, st>>>(p.partial, total_nq, t_split, fwd_best,
                                                                 fwd_second);
     B2S_CUDA(cudaGetLastError());
+    note_launch();
   }
   return B2S_OK;
 }

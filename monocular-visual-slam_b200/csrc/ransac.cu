@@ -142,18 +142,23 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-// Null vector of an 8x9 matrix by Gauss-Jordan elimination with complete pivoting.
-__device__ void null_vector_8x9(double (*A)[9], double* v) {
-  int perm[9];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) perm[c] = c;
+// Null vector of an 8x9 matrix: Gaussian elimination with complete pivoting + back
+// substitution.  The matrix lives in shared memory, element-major ([r*9+c][thread]), so
+// the dynamically indexed accesses complete pivoting needs are bank-conflict free and
+// never touch local memory (the first version kept A in local memory and was 12x off the
+// FP64 pipe bound, stalled on long-scoreboard).
+constexpr int kEpThreads = 64;
+#define A_(r, c) sA[((r) * 9 + (c)) * kEpThreads]
+
+__device__ void null_vector_8x9(double* sA /* already offset by threadIdx.x */, double* v) {
+  uint64_t perm = 0x876543210ull;  // column permutation, one nibble per column (stays in registers)
   int rank = 8;
   for (int k = 0; k < 8; ++k) {
     int pr = k, pc = k;
     double big = 0.0;
     for (int r = k; r < 8; ++r)
       for (int c = k; c < 9; ++c) {
-        const double a = fabs(A[r][c]);
+        const double a = fabs(A_(r, c));
         if (a > big) {
           big = a;
           pr = r;
@@ -164,39 +169,59 @@ __device__ void null_vector_8x9(double (*A)[9], double* v) {
       rank = k;
       break;
     }
-    if (pr != k)
-      for (int c = 0; c < 9; ++c) {
-        const double tmp = A[k][c];
-        A[k][c] = A[pr][c];
-        A[pr][c] = tmp;
-      }
-    if (pc != k) {
+    if (pc != k) {  // column swap touches every row (back substitution reads the upper part)
       for (int r = 0; r < 8; ++r) {
-        const double tmp = A[r][k];
-        A[r][k] = A[r][pc];
-        A[r][pc] = tmp;
+        const double tmp = A_(r, k);
+        A_(r, k) = A_(r, pc);
+        A_(r, pc) = tmp;
       }
-      const int tp = perm[k];
-      perm[k] = perm[pc];
-      perm[pc] = tp;
+      const uint64_t a = (perm >> (4 * k)) & 15ull, b = (perm >> (4 * pc)) & 15ull;
+      perm ^= ((a ^ b) << (4 * k)) | ((a ^ b) << (4 * pc));
     }
-    const double inv = 1.0 / A[k][k];
-    for (int c = k; c < 9; ++c) A[k][c] *= inv;
-    for (int r = 0; r < 8; ++r) {
-      if (r == k) continue;
-      const double f = A[r][k];
-      if (f != 0.0)
-        for (int c = k; c < 9; ++c) A[r][c] = fma(-f, A[k][c], A[r][c]);
+    double prow[9];  // pivot row (columns k..8), swapped into place on the fly
+    double piv = 1.0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      if (c >= k) {
+        prow[c] = A_(pr, c);
+        if (pr != k) {
+          A_(pr, c) = A_(k, c);
+          A_(k, c) = prow[c];
+        }
+        if (c == k) piv = prow[c];
+      }
+    }
+    const double inv = 1.0 / piv;
+    for (int r = k + 1; r < 8; ++r) {
+      const double f = A_(r, k) * inv;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+        if (c > k) A_(r, c) = fma(-f, prow[c], A_(r, c));
     }
   }
-  // free variable = column `rank` (permuted); pivots 0..rank-1 solve against it
-  for (int c = 0; c < 9; ++c) v[c] = 0.0;
-  v[perm[rank]] = 1.0;
-  for (int k = 0; k < rank; ++k) v[perm[k]] = -A[k][rank];
+  // back substitution in permuted column order: x[8] = 1, free x[rank..7] = 0
+  double x[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) x[c] = (c == 8) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 7; k >= 0; --k) {
+    if (k < rank) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+        if (c > k) acc = fma(A_(k, c), x[c], acc);
+      x[k] = -acc / A_(k, k);
+    }
+  }
   double n2 = 0.0;
-  for (int c = 0; c < 9; ++c) n2 = fma(v[c], v[c], n2);
-  const double s = rsqrt(n2);
-  for (int c = 0; c < 9; ++c) v[c] *= s;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) n2 = fma(x[c], x[c], n2);
+  const double sc = rsqrt(n2);
+  // un-permute through shared memory (row 0 is dead now) to avoid a dynamically indexed local array
+#pragma unroll
+  for (int c = 0; c < 9; ++c) A_(0, (int)((perm >> (4 * c)) & 15ull)) = x[c] * sc;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) v[c] = A_(0, c);
 }
 
 // Smallest-eigenvalue eigenvector of the symmetric 3x3 S (cyclic Jacobi).
@@ -230,16 +255,19 @@ __device__ void smallest_eigvec3(double S[3][3], double* out) {
       }
     }
   }
-  int mi = 0;
-  if (S[1][1] < S[mi][mi]) mi = 1;
-  if (S[2][2] < S[mi][mi]) mi = 2;
-  for (int k = 0; k < 3; ++k) out[k] = V[k][mi];
+  // static selects (a dynamically indexed V[k][mi] would push S and V to local memory)
+  const bool use1 = S[1][1] < S[0][0];
+  const double m01 = use1 ? S[1][1] : S[0][0];
+  const bool use2 = S[2][2] < m01;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[k] = use2 ? V[k][2] : (use1 ? V[k][1] : V[k][0]);
 }
 
-__global__ void __launch_bounds__(128) eight_point_kernel(
+__global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count, int H,
     const int32_t* __restrict__ samples_in, uint64_t seed, int32_t* __restrict__ samples_out, const Mat3 K,
     const Mat3 Kinv, double* __restrict__ E_out) {
+  __shared__ double s_A[72 * kEpThreads];  // 36 KB: one 8x9 system per thread, element-major
   const int pair = blockIdx.y;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
@@ -273,7 +301,7 @@ __global__ void __launch_bounds__(128) eight_point_kernel(
     return;
   }
 
-  double A[8][9];
+  double* sA = &s_A[threadIdx.x];
   for (int k = 0; k < 8; ++k) {
     const float4 c = cp[idx[k]];
     const double sx = c.x, sy = c.y, dx = c.z, dy = c.w;
@@ -285,12 +313,12 @@ __global__ void __launch_bounds__(128) eight_point_kernel(
     const double w2 = fma(ki[6], dx, fma(ki[7], dy, ki[8]));
     const double u = fma(ki[0], dx, fma(ki[1], dy, ki[2])) / w2;
     const double v = fma(ki[3], dx, fma(ki[4], dy, ki[5])) / w2;
-    A[k][0] = u * x; A[k][1] = u * y; A[k][2] = u;
-    A[k][3] = v * x; A[k][4] = v * y; A[k][5] = v;
-    A[k][6] = x;     A[k][7] = y;     A[k][8] = 1.0;
+    A_(k, 0) = u * x; A_(k, 1) = u * y; A_(k, 2) = u;
+    A_(k, 3) = v * x; A_(k, 4) = v * y; A_(k, 5) = v;
+    A_(k, 6) = x;     A_(k, 7) = y;     A_(k, 8) = 1.0;
   }
   double f[9];
-  null_vector_8x9(A, f);
+  null_vector_8x9(sA, f);
 
   // rank-2 projection: F' = F - (F v3) v3^T, v3 = right-singular vector of the smallest
   // singular value (homography.py:244-246 zeroes S[2] only).
@@ -332,10 +360,11 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
     K.m[i] = K_host ? K_host[i] : ((i % 4 == 0) ? 1.0 : 0.0);
     Kinv.m[i] = Kinv_host ? Kinv_host[i] : ((i % 4 == 0) ? 1.0 : 0.0);
   }
-  dim3 grid((H + 127) / 128, n_pairs);
-  eight_point_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  dim3 grid((H + kEpThreads - 1) / kEpThreads, n_pairs);
+  eight_point_kernel<<<grid, kEpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(corr), c_off, c_count, H, samples_in, seed, samples_out, K, Kinv, E_out);
   B2S_CUDA(cudaGetLastError());
+  note_launch();
   return B2S_OK;
 }
 
@@ -356,6 +385,7 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
   else
     ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
   B2S_CUDA(cudaGetLastError());
+  note_launch();
   return B2S_OK;
 }
 
@@ -370,6 +400,7 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
       counts, reinterpret_cast<const float4*>(corr), c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count,
       inlier_mask);
   B2S_CUDA(cudaGetLastError());
+  note_launch();
   return B2S_OK;
 }
 

@@ -161,5 +161,6 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
   }
   select_matches_kernel<<<n_pairs, threads, smem, st>>>(p, lut);
   B2S_CUDA(cudaGetLastError());
+  note_launch();
   return B2S_OK;
 }

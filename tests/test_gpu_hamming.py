@@ -194,3 +194,51 @@ def test_bad_arguments_raise(matcher):
         matcher.knn2_pairs([np.zeros((3, 32), np.float32)], [np.zeros((3, 32), np.uint8)])
     with pytest.raises(ValueError):
         matcher.knn2_pairs([np.zeros((3, 64), np.uint8)], [np.zeros((3, 64), np.uint8)])
+
+
+# ---- K2: tcgen05 kind::i8 variant, same contract, same bit-exact bar -------------------
+
+@pytest.fixture(scope="module")
+def matcher_i8():
+    from b200slam import _capi
+    from b200slam.frontend import HammingMatcher
+    return HammingMatcher(variant=_capi.VARIANT_I8MMA)
+
+
+def test_i8_variant_golden_bit_exact(hg, matcher_i8):
+    names = list(hg["names"])
+    out = matcher_i8.knn2_pairs([hg[f"{n}/q"] for n in names], [hg[f"{n}/t"] for n in names])
+    for n, (fb, fs, bb) in zip(names, out):
+        b, s, bw = ho.packed_keys(_pad(hg[f"{n}/q"]), _pad(hg[f"{n}/t"]))
+        np.testing.assert_array_equal(fb, b, err_msg=n)
+        np.testing.assert_array_equal(fs, s, err_msg=n)
+        np.testing.assert_array_equal(bb, bw, err_msg=n)
+
+
+def test_i8_variant_ragged_and_large(matcher_i8, matcher):
+    rng = np.random.default_rng(21)
+    sizes = [(int(rng.integers(1, 900)), int(rng.integers(1, 900))) for _ in range(10)] + [(0, 7), (7, 0), (128, 128), (129, 127), (2000, 2000), (1944, 2000)]
+    for alphabet in (256, 4):
+        qs = [rng.integers(0, alphabet, (a, 32), dtype=np.uint8) for a, _ in sizes]
+        ts = [rng.integers(0, alphabet, (b, 32), dtype=np.uint8) for _, b in sizes]
+        got = matcher_i8.knn2_pairs(qs, ts)
+        want = matcher.knn2_pairs(qs, ts)          # K1, itself pinned to the oracle above
+        for (fb, fs, bb), (wb, ws, wbb), sz in zip(got, want, sizes):
+            np.testing.assert_array_equal(fb, wb, err_msg=str(sz))
+            np.testing.assert_array_equal(fs, ws, err_msg=str(sz))
+            np.testing.assert_array_equal(bb, wbb, err_msg=str(sz))
+    q, t = qs[-2], ts[-2]
+    b, s, bw = ho.packed_keys(q, t)
+    np.testing.assert_array_equal(got[-2][0], b)
+    np.testing.assert_array_equal(got[-2][2], bw)
+
+
+def test_i8_variant_pipeline_front_doors(hg, matcher_i8):
+    names = ["noisy_2000x2000", "orb_real_0", "duplicates_70x70", "identical_50"]
+    qs, ts = [hg[f"{n}/q"] for n in names], [hg[f"{n}/t"] for n in names]
+    out = matcher_i8.match_pairs(qs, ts, use_ratio=False, use_cross=True, sort_by_distance=True, max_matches=500)
+    for n, (qi, ti, d) in zip(names, out):
+        key = f"{n}/pipe_c1_r0.8_m500"
+        np.testing.assert_array_equal(qi, hg[key + "_q"], err_msg=key)
+        np.testing.assert_array_equal(ti, hg[key + "_t"], err_msg=key)
+        np.testing.assert_array_equal(d, hg[key + "_d"], err_msg=key)
