@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="CPU baseline sample size (0 = one per core, min 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="i8", choices=["popc", "i8"], help="Hamming kernel: K1 POPC or K2 tcgen05 kind::i8")
+    ap.add_argument("--chunks", type=int, default=4, help="e2e: copy/compute overlap chunks")
     ap.add_argument("--sweep", action="store_true", help="also time every POPC-kernel configuration (extra key)")
     return ap.parse_args()
 
@@ -64,13 +65,13 @@ def workload_config(a, world):
 # ------------------------------------------------------------------------------------ #
 
 def cpu_arm(a, n_pairs, steps=1, warmup=0):
-    from b200slam.synthetic import tracking_pairs
+    from b200slam.synthetic import tracking_sequence
     from oracle import reference_path as rp
 
     cores = os.cpu_count() or 1
     n_pairs = n_pairs or max(8, cores)
-    qs, ts, kq, kt = tracking_pairs(n_pairs, a.nfeat, seed=1234)
-    pairs = list(zip(qs, ts, kq, kt))
+    desc, kp = tracking_sequence(n_pairs + 1, a.nfeat, seed=1234)          # the same sequence the GPU arm tracks
+    pairs = [(desc[k], desc[k + 1], kp[k], kp[k + 1]) for k in range(n_pairs)]
     for _ in range(warmup):
         rp.run_pairs(pairs[: max(1, min(len(pairs), cores))], workers=cores, max_iter=a.hyps)
     times, res = [], None
@@ -151,7 +152,7 @@ def b200_main(a):
 
     from b200slam import _capi
     from b200slam.frontend import Frontend, FrontendConfig, PairBatch, pipe_microbench
-    from b200slam.synthetic import tracking_pairs
+    from b200slam.synthetic import tracking_sequence
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,15 +164,18 @@ def b200_main(a):
     dev = torch.device("cuda", local)
     lib = _capi.load_library()
 
-    # ---- synthetic batch: generate a few distinct pairs on the host, tile to the batch size ----
-    base = min(a.pairs, 16)
-    qs, ts, kq, kt = tracking_pairs(base, a.nfeat, seed=1234 + rank)
-    reps = (a.pairs + base - 1) // base
-    qs, ts, kq, kt = [(x * reps)[: a.pairs] for x in (qs, ts, kq, kt)]
+    # ---- synthetic SEQUENCE: pairs+1 frames, consecutive pairs share frames (uploaded once) ----
+    from b200slam.frontend import SequenceTracker, sequence_batch
+    desc_np, kp_np = tracking_sequence(a.pairs + 1, a.nfeat, seed=1234 + rank)
+    counts = np.full(a.pairs + 1, a.nfeat, np.int32)
     cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337 + rank)
     variant = _capi.VARIANT_I8MMA if a.variant == "i8" else _capi.VARIANT_POPC
     fe = Frontend(cfg, variant=variant)
-    batch = PairBatch.from_host(qs, ts, kq, kt, device=dev)
+    desc_host = torch.from_numpy(desc_np.reshape(-1, 32)).pin_memory()
+    kp_host = torch.from_numpy(kp_np.reshape(-1, 2)).pin_memory()
+    desc_dev, kp_dev = desc_host.to(dev), kp_host.to(dev)
+    batch = sequence_batch(desc_dev, kp_dev, counts, 0, a.pairs, a.nfeat)     # inputs resident in HBM
+    qs = ts = [None] * a.pairs
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     pair_ids = torch.arange(rank * a.pairs, (rank + 1) * a.pairs, dtype=torch.int32, device=dev)
@@ -231,20 +235,24 @@ def b200_main(a):
     other = HammingMatcher(variant=_capi.VARIANT_POPC if a.variant == "i8" else _capi.VARIANT_I8MMA)
     other_avg = float(np.mean(timed(lambda: other.knn2(batch), max(3, a.steps // 2), 2))) * 1e-3
     variants_ms = {a.variant: k1_avg * 1e3, ("popc" if a.variant == "i8" else "i8"): other_avg * 1e3}
-    popc_ops = 8.0 * sum(len(q) * len(t) for q, t in zip(qs, ts))          # algorithmic POPC32 per launch
+    popc_ops = 8.0 * float(a.pairs) * a.nfeat * a.nfeat                    # algorithmic POPC32 per launch
     alg_bytes = float(batch.total_nq + batch.total_nt) * 32 + 4.0 * (2 * batch.total_nq + batch.total_nt)
 
-    # ---- end to end through host buffers (pinned host -> device -> kernels -> host) ----
-    host = HostStage(batch, qs, ts, kq, kt, torch, dev)
+    # ---- end to end through host buffers: pinned host frames -> device -> kernels -> pinned host ----
+    tracker = SequenceTracker(a.pairs + 1, a.nfeat, cfg, variant=variant, chunks=a.chunks, device=dev)
+    tracker.fe = fe
 
     def e2e_step():
-        host.upload()
-        res = fe.run(host.batch)
-        host.download(res)
+        out = tracker.run(desc_host, kp_host, counts)
         if world > 1:
-            rec = torch.stack([res.sel.count, res.best_h, res.best_count, pair_ids], dim=1).contiguous()
-            _allgather(rec)
+            rec = torch.stack([tracker._keep[-1].sel.count, tracker._keep[-1].best_h, tracker._keep[-1].best_count,
+                               pair_ids[: tracker._keep[-1].best_h.numel()]], dim=1).contiguous()
+            dist.all_gather_into_tensor(gather_small, rec)
         torch.cuda.current_stream().synchronize()
+        return out
+    if world > 1:
+        lo, hi = tracker.bounds[-1]
+        gather_small = torch.empty((world * (hi - lo), 4), dtype=torch.int32, device=dev)
     e2e_ms = timed(e2e_step, a.steps, a.warmup)
     e2e_total = float(np.sum(e2e_ms))
     if world > 1:
@@ -294,7 +302,7 @@ def b200_main(a):
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 popcount + f64 Sampson", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clk, "roofline": roof,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": len(tracker.bounds),
                     "ms_per_step": e2e_total / a.steps},
             "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
             "kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
@@ -332,46 +340,6 @@ def sweep(lib, fe, batch, timed, a):
                 out[f"csa{csa}_r{rows}_w{warps}"] = float(np.mean(timed(lambda: fe.matcher.knn2(batch), 5, 2)))
     lib.b2s_hamming_set_config(*keep)
     return out
-
-
-class HostStage:
-    """Pinned host staging for the end-to-end number: descriptors + keypoints go up every
-    step; match triplets, counts, winners and inlier masks come back every step."""
-
-    def __init__(self, batch, qs, ts, kq, kt, torch, dev):
-        import copy
-        self.torch = torch
-        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
-        self.h = {"q": pin(np.concatenate(qs)), "t": pin(np.concatenate(ts)), "kq": pin(np.concatenate(kq)), "kt": pin(np.concatenate(kt))}
-        self.batch = copy.copy(batch)
-        self.batch.q_desc = torch.empty_like(batch.q_desc)
-        self.batch.t_desc = torch.empty_like(batch.t_desc)
-        self.batch.kp_q = torch.empty_like(batch.kp_q)
-        self.batch.kp_t = torch.empty_like(batch.kp_t)
-        n, nq = batch.n_pairs, batch.total_nq
-        self.o = {"count": torch.empty(n, dtype=torch.int32).pin_memory(), "best_h": torch.empty(n, dtype=torch.int32).pin_memory(),
-                  "best_count": torch.empty(n, dtype=torch.int32).pin_memory(),
-                  "out_q": torch.empty(nq, dtype=torch.int32).pin_memory(), "out_t": torch.empty(nq, dtype=torch.int32).pin_memory(),
-                  "out_d": torch.empty(nq, dtype=torch.int32).pin_memory(), "mask": torch.empty(nq, dtype=torch.uint8).pin_memory()}
-        self.h2d_bytes = int(sum(v.numel() * v.element_size() for v in self.h.values()))
-        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.o.values()))
-
-    def upload(self):
-        b = self.batch
-        b.q_desc.copy_(self.h["q"], non_blocking=True)
-        b.t_desc.copy_(self.h["t"], non_blocking=True)
-        b.kp_q.copy_(self.h["kq"], non_blocking=True)
-        b.kp_t.copy_(self.h["kt"], non_blocking=True)
-
-    def download(self, res):
-        o = self.o
-        o["count"].copy_(res.sel.count, non_blocking=True)
-        o["best_h"].copy_(res.best_h, non_blocking=True)
-        o["best_count"].copy_(res.best_count, non_blocking=True)
-        o["out_q"].copy_(res.sel.out_q, non_blocking=True)
-        o["out_t"].copy_(res.sel.out_t, non_blocking=True)
-        o["out_d"].copy_(res.sel.out_d, non_blocking=True)
-        o["mask"].copy_(res.inlier_mask, non_blocking=True)
 
 
 def main():

@@ -70,7 +70,7 @@ int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz)
  * b2s_hamming_workspace_bytes(total_nq, t_split_max) bytes when t_split != 1. */
 size_t b2s_hamming_workspace_bytes(int total_nq, int t_split);
 /* Workspace of either variant.  The I8MMA variant stages every descriptor as 256 int8
- * (+1/-1) in 32 KB operand tiles: n_pairs * (ceil(max_nq/128) + ceil(max_nt/128)) * 32 KB,
+ * (+1/-1) in 40 KB operand tiles: n_pairs * (ceil(max_nq/128) + ceil(max_nt/128)) * 40 KB,
  * 128-byte aligned; t_split is ignored by it. */
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt,
                                      int t_split);
@@ -95,15 +95,20 @@ int b2s_hamming_get_config(int* csa_level, int* rows_per_thread, int* warps);
  *   use_cross: keep iff index(bwd_best[j]) == i
  *   sort_by_distance: stable sort by distance (ties ascending queryIdx), else ascending queryIdx
  *   max_matches: > 0 truncates, 0 = keep all
- *   kp_q/kp_t: optional (total, 2) float32 keypoint coordinates; when both given,
- *              out_corr[(q_off[p]+k)*4 .. +3] = (x1, y1, x2, y2) of match k
- *              (matches_to_points, feature_pipeline.py.bak:104-111)
- * Outputs for pair p live at [q_off[p], q_off[p] + out_count[p]). */
+ *   kp_q/kp_t: optional (rows, 2) float32 keypoint coordinates; when both given,
+ *              out_corr[(base+k)*4 .. +3] = (x1, y1, x2, y2) of match k
+ *              (matches_to_points, feature_pipeline.py.bak:104-111).  kp_*_src_row
+ *              (device, n_pairs int32, or NULL): first keypoint row of pair p when it is
+ *              not the CSR offset (shared frames, as q_src_row/t_src_row above).
+ *   out_stride: 0 -> pair p's outputs live at [q_off[p], q_off[p] + out_count[p]);
+ *              > 0 -> at [p*out_stride, p*out_stride + out_count[p]) (compact layout for
+ *              truncated selections; a pair that does not fit gets out_count = -1). */
 int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_second,
                        const uint32_t* bwd_best, const int32_t* q_off, const int32_t* t_off,
                        int n_pairs, int max_nq, int use_ratio, int use_cross,
                        const int32_t* ratio_lut_host, int sort_by_distance, int max_matches,
-                       const float* kp_q, const float* kp_t, int32_t* out_q, int32_t* out_t,
+                       const float* kp_q, const float* kp_t, const int32_t* kp_q_src_row,
+                       const int32_t* kp_t_src_row, int out_stride, int32_t* out_q, int32_t* out_t,
                        int32_t* out_d, float* out_corr, int32_t* out_count, void* stream);
 
 /* ---- K4: batched 8-point minimal solver ---------------------------------------
@@ -143,7 +148,7 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
 
 /* ---- measurement helper ----------------------------------------------------------
  * Saturates one SM pipe with independent instructions to measure its rate:
- * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD.
+ * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD, 7 REDUX.MIN, 8 SHFL.
  * Launches ctas_per_sm*SMs CTAs of 256 threads doing `iters` x 64 instructions per
  * thread; *ops_out = total thread-level instructions executed (the caller times it). */
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink,

@@ -24,7 +24,7 @@ SELECT_MAX_QUERIES = 32768
 VARIANT_POPC = 0
 VARIANT_I8MMA = 1
 
-PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "imad": 6}
+PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "imad": 6, "redux": 7, "shfl": 8}
 
 
 class B2SError(RuntimeError):
@@ -59,7 +59,7 @@ def _declare(lib):
     lib.b2s_hamming_get_config.argtypes = [ip, ip, ip]
     lib.b2s_select_matches.restype = i32
     lib.b2s_select_matches.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32,
-                                       vp, vp, vp, vp, vp, vp, vp, vp]
+                                       vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.b2s_eight_point_batched.restype = i32
     lib.b2s_eight_point_batched.argtypes = [vp, vp, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]
     lib.b2s_ransac_score_batched.restype = i32

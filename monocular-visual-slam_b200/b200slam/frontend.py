@@ -110,6 +110,28 @@ class PairBatch:
             q_off_host=q_off, t_off_host=t_off, kp_q=kp_q, kp_t=kp_t)
 
 
+def sequence_batch(desc_dev, kp_dev, counts: np.ndarray, first_pair: int, n_pairs: int, frame_rows: int) -> PairBatch:
+    """Consecutive-frame pairs (frame k, frame k+1) over frames that were uploaded ONCE:
+    descriptors/keypoints of frame f start at row f*frame_rows of desc_dev / kp_dev; pair p
+    matches frame first_pair+p (query) against frame first_pair+p+1 (train) through the
+    q_src/t_src row indirection, so no descriptor is copied or stored twice."""
+    torch = _capi.require_cuda()
+    dev = desc_dev.device
+    nq = counts[first_pair:first_pair + n_pairs].astype(np.int32)
+    nt = counts[first_pair + 1:first_pair + n_pairs + 1].astype(np.int32)
+    q_off = np.zeros(n_pairs + 1, np.int32)
+    t_off = np.zeros(n_pairs + 1, np.int32)
+    np.cumsum(nq, out=q_off[1:])
+    np.cumsum(nt, out=t_off[1:])
+    q_src = (np.arange(first_pair, first_pair + n_pairs, dtype=np.int64) * frame_rows).astype(np.int32)
+    t_src = q_src + np.int32(frame_rows)
+    pack = torch.from_numpy(np.concatenate([q_off, t_off, q_src, t_src])).to(dev)
+    n1 = n_pairs + 1
+    return PairBatch(q_desc=desc_dev, t_desc=desc_dev, q_off=pack[:n1], t_off=pack[n1:2 * n1],
+                     q_off_host=q_off, t_off_host=t_off, kp_q=kp_dev, kp_t=kp_dev,
+                     q_src=pack[2 * n1:2 * n1 + n_pairs], t_src=pack[2 * n1 + n_pairs:])
+
+
 @dataclass
 class Keys:
     fwd_best: "torch.Tensor"
@@ -119,11 +141,16 @@ class Keys:
 
 @dataclass
 class Selection:
+    """Selected matches.  Pair p's entries live at [c_off[p], c_off[p] + count[p]) of
+    out_q / out_t / out_d / corr: CSR over the query rows (stride 0) or the compact layout
+    p * stride (stride = max_matches) that keeps device->host copies small."""
     out_q: "torch.Tensor"
     out_t: "torch.Tensor"
     out_d: "torch.Tensor"
     count: "torch.Tensor"
     corr: "torch.Tensor | None"
+    c_off: "torch.Tensor"
+    stride: int = 0
 
 
 class HammingMatcher:
@@ -135,6 +162,7 @@ class HammingMatcher:
         self.t_split = t_split
         self._lib = _capi.load_library()
         self._ws = None
+        self._coff = {}
 
     def knn2(self, b: PairBatch) -> Keys:
         torch = _capi.require_cuda()
@@ -160,26 +188,37 @@ class HammingMatcher:
 
     def select(self, b: PairBatch, k: Keys, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
                sort_by_distance: bool = True, max_matches: int | None = None,
-               with_corr: bool = False) -> Selection:
+               with_corr: bool = False, compact: bool = False) -> Selection:
         torch = _capi.require_cuda()
         dev = b.q_desc.device
         nq = b.total_nq
-        oq = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
-        ot = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
-        od = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        stride = int(max_matches) if (compact and max_matches) else 0
+        rows = b.n_pairs * stride if stride else nq
+        oq = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+        ot = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+        od = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
         cnt = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev)
         corr = None
         if with_corr:
             if b.kp_q is None or b.kp_t is None:
                 raise ValueError("with_corr needs keypoint coordinates in the batch")
-            corr = torch.empty((max(nq, 1), 4), dtype=torch.float32, device=dev)
+            corr = torch.empty((max(rows, 1), 4), dtype=torch.float32, device=dev)
+        if stride:
+            key = (str(dev), b.n_pairs, stride)
+            if key not in self._coff:
+                self._coff[key] = (torch.arange(b.n_pairs + 1, dtype=torch.int32, device=dev) * stride).contiguous()
+            c_off = self._coff[key]
+        else:
+            c_off = b.q_off
         lut = ratio_lut(ratio) if use_ratio else None
         check(self._lib.b2s_select_matches(
             ptr(k.fwd_best), ptr(k.fwd_second), ptr(k.bwd_best), ptr(b.q_off), ptr(b.t_off),
             b.n_pairs, b.max_nq, int(use_ratio), int(use_cross), ptr(lut), int(sort_by_distance),
             int(max_matches or 0), ptr(b.kp_q) if with_corr else None, ptr(b.kp_t) if with_corr else None,
+            ptr(b.q_src) if with_corr else None, ptr(b.t_src) if with_corr else None, stride,
             ptr(oq), ptr(ot), ptr(od), ptr(corr), ptr(cnt), current_stream()))
-        return Selection(oq[:nq], ot[:nq], od[:nq], cnt[:b.n_pairs], None if corr is None else corr[:nq])
+        return Selection(oq[:rows], ot[:rows], od[:rows], cnt[:b.n_pairs], None if corr is None else corr[:rows],
+                         c_off, stride)
 
     # ---- host convenience: numpy in, numpy out (includes H2D / D2H) -------------------
     def match_pairs(self, q_list, t_list, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
@@ -302,13 +341,89 @@ class Frontend:
         c = self.cfg
         keys = self.matcher.knn2(b)
         sel = self.matcher.select(b, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
-                                  sort_by_distance=True, max_matches=c.max_matches, with_corr=True)
-        E = self.ransac.hypotheses(sel.corr, b.q_off, sel.count, b.n_pairs, c.hypotheses,
+                                  sort_by_distance=True, max_matches=c.max_matches, with_corr=True,
+                                  compact=True)
+        E = self.ransac.hypotheses(sel.corr, sel.c_off, sel.count, b.n_pairs, c.hypotheses,
                                    samples=samples, seed=c.seed, K=K)
         th2 = c.threshold ** 2
-        counts = self.ransac.score(sel.corr, b.q_off, sel.count, b.n_pairs, E, th2, precision=c.precision)
-        best_h, best_c, mask = self.ransac.select(counts, sel.corr, b.q_off, sel.count, b.n_pairs, E, th2)
+        counts = self.ransac.score(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, precision=c.precision)
+        best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
         return FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
+
+
+class SequenceTracker:
+    """End-to-end tracking of a frame sequence from HOST buffers (the e2e number of bench.py).
+
+    Frames (descriptors uint8 [F, N, 32], keypoints float32 [F, N, 2], pinned) are uploaded
+    once each; the F-1 consecutive pairs are processed in `chunks` pieces so the upload of
+    chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c (three streams).
+    Results land in pinned host buffers: per pair the match count, winning hypothesis and
+    inlier count, and per match (compact stride max_matches) queryIdx/trainIdx/distance/inlier.
+    """
+
+    def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA,
+                 chunks: int = 4, device=None):
+        torch = _capi.require_cuda()
+        if not cfg.max_matches:
+            raise ValueError("SequenceTracker needs max_matches (compact output stride)")
+        self.torch, self.cfg = torch, cfg
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.F, self.N = n_frames, frame_rows
+        self.n_pairs = n_frames - 1
+        self.fe = Frontend(cfg, variant=variant)
+        self.desc = torch.empty((n_frames * frame_rows, DESC_BYTES), dtype=torch.uint8, device=self.dev)
+        self.kp = torch.empty((n_frames * frame_rows, 2), dtype=torch.float32, device=self.dev)
+        chunks = max(1, min(chunks, self.n_pairs))
+        self.bounds = [(self.n_pairs * c // chunks, self.n_pairs * (c + 1) // chunks) for c in range(chunks)]
+        self.s_up, self.s_down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        P, S = self.n_pairs, cfg.max_matches
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.out = {"count": pin(P, torch.int32), "best_h": pin(P, torch.int32), "best_count": pin(P, torch.int32),
+                    "out_q": pin(P * S, torch.int32), "out_t": pin(P * S, torch.int32),
+                    "out_d": pin(P * S, torch.int32), "mask": pin(P * S, torch.uint8)}
+        self._batches = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.out.values()))
+
+    def run(self, desc_host, kp_host, counts: np.ndarray):
+        """desc_host: pinned uint8 [F*N, 32]; kp_host: pinned float32 [F*N, 2]; counts: rows used per frame."""
+        torch, N = self.torch, self.N
+        if self._batches is None or not np.array_equal(self._counts, counts):
+            self._counts = np.array(counts, copy=True)
+            self._batches = [sequence_batch(self.desc, self.kp, self._counts, lo, hi - lo, N) for lo, hi in self.bounds]
+        main = torch.cuda.current_stream()
+        self.s_up.wait_stream(main)
+        ups, keep = [], []
+        with torch.cuda.stream(self.s_up):
+            for c, (lo, hi) in enumerate(self.bounds):
+                f0 = lo if c == 0 else lo + 1                      # frame `lo` came with the previous chunk
+                r0, r1 = f0 * N, (hi + 1) * N
+                self.desc[r0:r1].copy_(desc_host[r0:r1], non_blocking=True)
+                self.kp[r0:r1].copy_(kp_host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_up)
+                ups.append(ev)
+        self.h2d_bytes = int(self.F * N * (DESC_BYTES + 8))
+        S = self.cfg.max_matches
+        for c, (lo, hi) in enumerate(self.bounds):
+            main.wait_event(ups[c])
+            res = self.fe.run(self._batches[c])
+            done = torch.cuda.Event()
+            done.record(main)
+            keep.append(res)
+            with torch.cuda.stream(self.s_down):
+                self.s_down.wait_event(done)
+                o = self.out
+                o["count"][lo:hi].copy_(res.sel.count, non_blocking=True)
+                o["best_h"][lo:hi].copy_(res.best_h, non_blocking=True)
+                o["best_count"][lo:hi].copy_(res.best_count, non_blocking=True)
+                o["out_q"][lo * S:hi * S].copy_(res.sel.out_q, non_blocking=True)
+                o["out_t"][lo * S:hi * S].copy_(res.sel.out_t, non_blocking=True)
+                o["out_d"][lo * S:hi * S].copy_(res.sel.out_d, non_blocking=True)
+                o["mask"][lo * S:hi * S].copy_(res.inlier_mask, non_blocking=True)
+        main.wait_stream(self.s_down)
+        self._keep = keep                                          # device tensors stay alive until the next run
+        return self.out
 
 
 def pipe_microbench(which: str, iters: int = 2000, ctas_per_sm: int = 8, repeats: int = 5):

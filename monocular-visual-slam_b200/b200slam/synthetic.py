@@ -52,3 +52,39 @@ def tracking_pairs(n_pairs: int, n_desc: int = 2000, seed: int = 1234, keep: flo
         qs.append(q), ts.append(tdesc)
         kq.append(n1[:, :2].astype(np.float32)), kt.append(n2[:, :2].astype(np.float32))
     return qs, ts, kq, kt
+
+
+def tracking_sequence(n_frames: int, n_desc: int = 2000, seed: int = 1234, keep: float = 0.7,
+                      flip: float = 0.08, pixel_noise: float = 0.5):
+    """A true frame SEQUENCE (BASELINE configs[1]): frame k+1 re-observes `keep` of frame k's
+    3-D points (descriptor copied with bit noise, rows permuted) under the camera motion
+    and replaces the rest.  -> (desc uint8 [F, N, 32], kp float32 [F, N, 2] normalised)."""
+    rng = np.random.default_rng(seed)
+    Kinv = np.linalg.inv(KITTI_K)
+    yaw = 0.02
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    t = np.array([0.05, 0.0, -1.0])
+
+    def fresh(n):
+        return (rng.integers(0, 256, (n, 32), dtype=np.uint8),
+                np.stack([rng.uniform(-10, 10, n), rng.uniform(-2, 2, n), rng.uniform(5, 40, n)], axis=1))
+
+    def observe(P):
+        uv = _project(P, np.eye(3), np.zeros(3), KITTI_K) + rng.normal(0, pixel_noise, (len(P), 2))
+        return (np.hstack([uv, np.ones((len(P), 1))]) @ Kinv.T)[:, :2].astype(np.float32)
+
+    desc = np.empty((n_frames, n_desc, 32), np.uint8)
+    kp = np.empty((n_frames, n_desc, 2), np.float32)
+    d, P = fresh(n_desc)
+    for f in range(n_frames):
+        desc[f], kp[f] = d, observe(P)
+        nd, nP = fresh(n_desc)
+        kept = rng.random(n_desc) < keep
+        Pm = P @ R.T + t                                   # same points in the next camera frame
+        kept &= Pm[:, 2] > 1.0                             # points that passed the camera are dropped
+        bits = np.unpackbits(d[kept], axis=1)
+        bits ^= (rng.random(bits.shape) < flip).astype(np.uint8)
+        slots = rng.permutation(n_desc)[: int(kept.sum())]
+        nd[slots], nP[slots] = np.packbits(bits, axis=1), Pm[kept]
+        d, P = nd, nP
+    return desc, kp

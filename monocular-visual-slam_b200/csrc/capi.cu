@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
         if (WHICH == 4) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[k]) : "d"(d[(k + 1) & 7]));
         if (WHICH == 5) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(f[(k + 1) & 7]));
         if (WHICH == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(c1), "r"(c2));
+        if (WHICH == 7) asm volatile("redux.sync.min.s32 %0, %0, 0xffffffff;" : "+r"(x[k]));
+        if (WHICH == 8) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x[k]));
       }
     }
   }
@@ -147,7 +149,7 @@ size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(which >= 0 && which <= 6, "which must be 0..6");
+  B2S_REQUIRE(which >= 0 && which <= 8, "which must be 0..8");
   B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
   const int grid = sm_count() * ctas_per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -158,6 +160,8 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     case 3: pipe_kernel<3><<<grid, 256, 0, st>>>(iters, sink); break;
     case 4: pipe_kernel<4><<<grid, 256, 0, st>>>(iters, sink); break;
     case 5: pipe_kernel<5><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 7: pipe_kernel<7><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 8: pipe_kernel<8><<<grid, 256, 0, st>>>(iters, sink); break;
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }
   B2S_CUDA(cudaGetLastError());

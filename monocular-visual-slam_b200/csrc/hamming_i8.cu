@@ -3,10 +3,16 @@
 // Same contract as K1 (hamming_popc.cu); replaces the same reference calls
 // (/root/reference/feature_pipeline.py.bak:68,82,84; homography.py:12-15,21-23).
 //
-// Hamming as a dense contraction: map bit b -> 1 - 2b (int8 +-1); then for two 256-bit
-// descriptors  dot = 256 - 2*ham, so  key = ham<<22 | idx = dot * (-2^21) + (2^29 + idx)
-// exactly (dot is even).  tcgen05.mma kind::i8 (M=128, N=128, K=32 per instruction, int32
-// accumulators in TMEM) produces a 128x128 tile of dots in 8 instructions.
+// Hamming as a dense contraction whose result already IS the sort key.  Query bits map to
+// +-64 (bit b -> 64(1-2b)), train bits to -+64, so a 256-byte dot product is
+// 8192*ham - 2^20 exactly.  One more K-step multiplies a constant "ones" slice [1, 64, 0..]
+// of the A-side tile with an "index" slice [j & 63, j >> 6, 0..] of the B-side tile
+// (j = row mod 8192), adding the row index:   acc = 8192*ham + j - 2^20.
+// Signed min over accumulators is therefore the lexicographic (distance, index) minimum —
+// OpenCV's tie rule — and the epilogue needs no key arithmetic at all, only min/max.
+// tcgen05.mma kind::i8 (M=128, N=128, K=32 per instruction, int32 accumulators in TMEM)
+// produces a 128x128 tile in 9 instructions.  Indices wrap every 8192 rows, so running
+// minima are flushed into the global packed-key domain at 8192-row window boundaries.
 //
 // Two products per tile pair so that BOTH reductions are per-thread (a TMEM lane is a
 // matrix row and each epilogue thread owns one lane):
@@ -16,56 +22,71 @@
 // layout), only the A/B descriptor roles swap.
 //
 // Pipeline (one CTA = one (pair, 128-query tile), 320 threads):
-//   warp 0   producer : cp.async.bulk (TMA engine) of pre-expanded 32 KB operand tiles into
+//   warp 0   producer : cp.async.bulk (TMA engine) of pre-expanded 40 KB operand tiles into
 //                       a 4-stage ring, mbarrier expect_tx / complete_tx
-//   warp 1   MMA      : one thread issues 16 tcgen05.mma per train tile, tcgen05.commit
+//   warp 1   MMA      : one thread issues 18 tcgen05.mma per train tile, tcgen05.commit
 //                       releases the smem stage and publishes the TMEM accumulator stage
-//   warps 2-9 epilogue: tcgen05.ld 32x32b.x32 (thread = TMEM lane), IMAD to a packed key,
-//                       4-way interleaved top-2 / min chains, merge, atomicMin for columns
+//   warps 2-9 epilogue: tcgen05.ld 32x32b.x32 (thread = TMEM lane), 4-way interleaved
+//                       top-2 chains at 2.5 min/max per element (pairs + VIMNMX3), 3-input
+//                       mins for the column direction, atomicMin for columns
 // TMEM: 2 accumulator stages x (D1 128 cols + D2 128 cols) = 512 columns.
 #include "common.cuh"
 
 namespace b2s {
 
-constexpr int kI8Tile = 128;                 // rows per operand tile
-constexpr int kI8TileBytes = kI8Tile * 256;  // 32 KB of +-1 int8
+constexpr int kI8Tile = 128;                      // rows per operand tile
+constexpr int kI8Chunks = 20;                     // 16-byte k-chunks per row: 16 data + ones(2) + index(2)
+constexpr int kI8ChunkBytes = kI8Tile * 16;       // 2048: one k-chunk of all 128 rows (= LBO)
+constexpr int kI8TileBytes = kI8Chunks * kI8ChunkBytes;  // 40 KB
+constexpr int kI8Units = kI8Chunks * kI8Tile;     // 16-byte units per tile
 constexpr int kI8Stages = 4;
 constexpr int kI8Threads = 320;
-constexpr uint32_t kKeyScale = 1u << 21;     // key = dot * (-2^21) + 2^29 + idx
-constexpr uint32_t kKeyBias = 1u << 29;
+constexpr int kWinBits = 13;                      // index window: 8192 rows
+constexpr int kWin = 1 << kWinBits;
+constexpr int kAccBias = 1 << 20;                 // acc + 2^20 = ham << 13 | (row mod 8192)
+constexpr int kAccNone = 0x7FFFFFFF;
 
-// ---- pre-pass: 256 bits -> 256 int8 (+1 / -1) in the UMMA canonical K-major layout ------
-// Tile = 128 rows x 256 bytes.  16-byte unit (row r, k-chunk kc) sits at unit index
-// kc*128 + r: 8 rows x 16 B form one 128-byte core matrix, core matrices of 8-row groups
-// are 128 B apart (SBO), the 16 k-chunks are 2048 B apart (LBO).
-__device__ __forceinline__ uint32_t spread4(uint32_t nib) {
-  // bit i of nib -> byte i: 0x01 for a clear bit (+1), 0xFF for a set bit (-1)
-  return (((nib * 0x00204081u) & 0x01010101u) * 0xFEu) | 0x01010101u;
+// ---- pre-pass: 256 bits -> 256 int8 (+-64) + ones/index slices, UMMA canonical K-major layout
+// Tile = 128 rows x 20 k-chunks of 16 bytes.  Unit (row r, k-chunk kc) sits at unit index
+// kc*128 + r: 8 rows x 16 B form one 128-byte core matrix, 8-row groups are 128 B apart
+// (SBO), k-chunks 2048 B apart (LBO).
+__device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
+  const uint32_t sp = (nib * 0x00204081u) & 0x01010101u;  // bit i -> byte i (0 or 1)
+  // query: +64 / -64 for clear / set;  train: -64 / +64
+  return train ? (0xC0C0C0C0u - sp * 0x80u) : (0x40404040u + sp * 0x80u);
 }
 
-__global__ void __launch_bounds__(256) expand_pm1_kernel(const uint8_t* __restrict__ desc,
-                                                         const int32_t* __restrict__ off,
-                                                         const int32_t* __restrict__ src, int tiles_per_pair,
-                                                         uint4* __restrict__ out) {
+__global__ void __launch_bounds__(256) expand_pm64_kernel(const uint8_t* __restrict__ desc,
+                                                          const int32_t* __restrict__ off,
+                                                          const int32_t* __restrict__ src, int tiles_per_pair,
+                                                          int train, uint4* __restrict__ out) {
   const int pair = blockIdx.y;
   const int o = off[pair];
   const int n = off[pair + 1] - o;
   const int in0 = src ? src[pair] : o;
   const int u = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte unit within the pair's tiles
-  const int tile = u >> 11, w = u & 2047;
+  const int tile = u / kI8Units, w = u - tile * kI8Units;
   if (tile >= tiles_per_pair) return;
   if (tile * kI8Tile >= n) return;  // tile never read
   const int kc = w >> 7, r = w & 127;
   const int row = tile * kI8Tile + r;
   uint4 v = make_uint4(0, 0, 0, 0);
-  if (row < n) {
-    const uint32_t bits = *reinterpret_cast<const uint16_t*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES + 2 * kc);
-    v.x = spread4(bits & 15u);
-    v.y = spread4((bits >> 4) & 15u);
-    v.z = spread4((bits >> 8) & 15u);
-    v.w = spread4((bits >> 12) & 15u);
+  if (kc < 16) {
+    if (row < n) {
+      const uint32_t bits =
+          *reinterpret_cast<const uint16_t*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES + 2 * kc);
+      v.x = spread4(bits & 15u, train);
+      v.y = spread4((bits >> 4) & 15u, train);
+      v.z = spread4((bits >> 8) & 15u, train);
+      v.w = spread4((bits >> 12) & 15u, train);
+    }
+  } else if (kc == 16) {
+    v.x = 1u | (64u << 8);                               // ones slice: [1, 64, 0, ...]
+  } else if (kc == 18) {
+    const uint32_t j = (uint32_t)row & (uint32_t)(kWin - 1);
+    v.x = (j & 63u) | ((j >> 6) << 8);                   // index slice: [j & 63, j >> 6, 0, ...]
   }
-  out[((size_t)pair * tiles_per_pair + tile) * 2048 + w] = v;
+  out[((size_t)pair * tiles_per_pair + tile) * kI8Units + w] = v;
 }
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------
@@ -106,7 +127,7 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)(2048u >> 4) << 16;         // leading (K-direction) byte offset, bits [16,30)
+  d |= (uint64_t)(kI8ChunkBytes >> 4) << 16; // leading (K-direction) byte offset, bits [16,30)
   d |= (uint64_t)(128u >> 4) << 32;          // stride (8-row group) byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
   return d;                                  // base offset 0, layout type 0 = SWIZZLE_NONE
@@ -128,8 +149,8 @@ constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct I8Params {
-  const uint8_t* __restrict__ qx;  // expanded query tiles  [pair][q_tiles][32 KB]
-  const uint8_t* __restrict__ tx;  // expanded train tiles  [pair][t_tiles][32 KB]
+  const uint8_t* __restrict__ qx;  // expanded query tiles  [pair][q_tiles][40 KB]
+  const uint8_t* __restrict__ tx;  // expanded train tiles  [pair][t_tiles][40 KB]
   const int32_t* __restrict__ q_off;
   const int32_t* __restrict__ t_off;
   uint32_t* __restrict__ fwd_best;
@@ -138,32 +159,48 @@ struct I8Params {
   int q_tiles, t_tiles;
 };
 
-// keys of 32 accumulator columns (local column index c0 + k) folded into 4 interleaved
-// top-2 chains (ILP 4; a single chain would serialise on the 4-cycle ALU latency)
+// 32 accumulator columns folded into 4 interleaved top-2 chains (ILP 4; one chain would
+// serialise on the 4-cycle ALU latency).  Two columns per step: the two smallest of
+// {best, second, lo, hi} are min(best, lo) and min3(second, max(best, lo), hi) — 5 ops / 2.
 template <bool TAIL>
-__device__ __forceinline__ void fold_top2(const uint32_t (&v)[32], int c0, int valid, uint32_t (&b)[4],
-                                          uint32_t (&s)[4]) {
+__device__ __forceinline__ void fold_top2(const uint32_t (&v)[32], int c0, int valid, int (&b)[4], int (&s)[4]) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    uint32_t key = v[k] * (0u - kKeyScale) + (kKeyBias + (uint32_t)(c0 + k));
-    if (TAIL) key = (c0 + k < valid) ? key : kNone;
-    top2_insert(b[k & 3], s[k & 3], key);
+  for (int k = 0; k < 32; k += 2) {
+    int x0 = (int)v[k], x1 = (int)v[k + 1];
+    if (TAIL) {
+      x0 = (c0 + k < valid) ? x0 : kAccNone;
+      x1 = (c0 + k + 1 < valid) ? x1 : kAccNone;
+    }
+    const int c = (k >> 1) & 3;
+    const int lo = min(x0, x1), hi = max(x0, x1);
+    const int mb = max(b[c], lo);
+    b[c] = min(b[c], lo);
+    s[c] = min(min(s[c], mb), hi);
   }
 }
 template <bool TAIL>
-__device__ __forceinline__ void fold_min(const uint32_t (&v)[32], int c0, int valid, uint32_t (&m)[4]) {
+__device__ __forceinline__ void fold_min(const uint32_t (&v)[32], int c0, int valid, int (&m)[4]) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    uint32_t key = v[k] * (0u - kKeyScale) + (kKeyBias + (uint32_t)(c0 + k));
-    if (TAIL) key = (c0 + k < valid) ? key : kNone;
-    m[k & 3] = min(m[k & 3], key);
+  for (int k = 0; k < 32; k += 2) {
+    int x0 = (int)v[k], x1 = (int)v[k + 1];
+    if (TAIL) {
+      x0 = (c0 + k < valid) ? x0 : kAccNone;
+      x1 = (c0 + k + 1 < valid) ? x1 : kAccNone;
+    }
+    const int c = (k >> 1) & 3;
+    m[c] = min(min(m[c], x0), x1);  // VIMNMX3
   }
+}
+// accumulator domain -> packed key (distance << 22 | pair-local index)
+__device__ __forceinline__ uint32_t acc_to_key(int acc, int window_base) {
+  const uint32_t u = (uint32_t)(acc + kAccBias);
+  return ((u >> kWinBits) << kIdxBits) | ((u & (uint32_t)(kWin - 1)) + (uint32_t)window_base);
 }
 
 __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_q = smem;                           // 32 KB
-  uint8_t* s_t = smem + kI8TileBytes;            // kI8Stages x 32 KB
+  uint8_t* s_q = smem;                           // 40 KB
+  uint8_t* s_t = smem + kI8TileBytes;            // kI8Stages x 40 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kI8Stages) * kI8TileBytes);
   uint64_t* b_full = bars;                       // [kI8Stages]
   uint64_t* b_empty = bars + kI8Stages;          // [kI8Stages]
@@ -228,12 +265,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         tc_fence_after();
         const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
         const uint32_t d1 = tmem_base + (uint32_t)a * 256u, d2 = d1 + 128u;
+        // K = 32 bytes per instruction = two k-chunks = 4096 B apart (descriptor units of 16 B: 256).
+        // Step 8 pairs the A tile's ones slice (chunk 16) with the B tile's index slice (chunk 18).
+        constexpr uint64_t kOnes = 16u * (kI8ChunkBytes >> 4), kIndex = 18u * (kI8ChunkBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // K = 32 bytes per instruction = two k-chunks = 4096 B apart (>>4 = 256)
+        for (int k = 0; k < 8; ++k)
           tc_mma_i8(d1, qdesc + (uint64_t)k * 256u, tdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+        tc_mma_i8(d1, qdesc + kOnes, tdesc + kIndex, kIdescI8, 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           tc_mma_i8(d2, tdesc + (uint64_t)k * 256u, qdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+        tc_mma_i8(d2, tdesc + kOnes, qdesc + kIndex, kIdescI8, 1);
         tc_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
         tc_commit(&b_tfull[a]);  // accumulators complete
       }
@@ -246,6 +288,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int nq_valid = min(kI8Tile, nq - q0);
     uint32_t gbest = kNone, gsecond = kNone;
+    int b[4] = {kAccNone, kAccNone, kAccNone, kAccNone}, s2[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
+    const int q_window = q0 & ~(kWin - 1);
     for (int t = 0; t < n_tt; ++t) {
       const int a = t & 1;
       const int tbase = t * kI8Tile;
@@ -258,7 +302,6 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
       TMEM_LD_X32(c1, v0);
       TMEM_LD_X32(c1 + 32u, v1);
       tmem_ld_wait();
-      uint32_t b[4] = {kNone, kNone, kNone, kNone}, s2[4] = {kNone, kNone, kNone, kNone};
       if (nt_valid == kI8Tile) {
         fold_top2<false>(v0, half * 64, kI8Tile, b, s2);
         fold_top2<false>(v1, half * 64 + 32, kI8Tile, b, s2);
@@ -274,7 +317,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_tempty[a]);  // accumulator stage drained into registers
-      uint32_t m[4] = {kNone, kNone, kNone, kNone};
+      int m[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
       if (nq_valid == kI8Tile) {
         fold_min<false>(v0, half * 64, kI8Tile, m);
         fold_min<false>(v1, half * 64 + 32, kI8Tile, m);
@@ -282,14 +325,19 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         fold_min<true>(v0, half * 64, nq_valid, m);
         fold_min<true>(v1, half * 64 + 32, nq_valid, m);
       }
-      // merge the 4 chains, rebase local indices to pair-local ones
+      const int cm = min(min(m[0], m[1]), min(m[2], m[3]));
+      if (row < nt_valid && cm != kAccNone) atomicMin(&p.bwd_best[to + tbase + row], acc_to_key(cm, q_window));
+      // leave the accumulator domain when the train index window (8192 rows) ends
+      if (((t + 1) & (kWin / kI8Tile - 1)) == 0 || t == n_tt - 1) {
+        const int window_base = tbase & ~(kWin - 1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (b[k] != kNone) top2_insert(gbest, gsecond, b[k] + (uint32_t)tbase);
-        if (s2[k] != kNone) top2_insert(gbest, gsecond, s2[k] + (uint32_t)tbase);
+        for (int k = 0; k < 4; ++k) {
+          if (b[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(b[k], window_base));
+          if (s2[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(s2[k], window_base));
+          b[k] = kAccNone;
+          s2[k] = kAccNone;
+        }
       }
-      const uint32_t cm = min(min(m[0], m[1]), min(m[2], m[3]));
-      if (row < nt_valid && cm != kNone) atomicMin(&p.bwd_best[to + tbase + row], cm + (uint32_t)q0);
     }
     // the two column halves of a query row meet in shared memory
     if (half == 1) s_merge[row] = make_uint2(gbest, gsecond);
@@ -336,11 +384,11 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
   uint8_t* qx = static_cast<uint8_t*>(workspace);
   uint8_t* tx = qx + (size_t)n_pairs * qt * kI8TileBytes;
-  expand_pm1_kernel<<<dim3((qt * 2048 + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt,
-                                                                           reinterpret_cast<uint4*>(qx));
+  expand_pm64_kernel<<<dim3((qt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt, 0,
+                                                                                reinterpret_cast<uint4*>(qx));
   B2S_CUDA(cudaGetLastError());
-  expand_pm1_kernel<<<dim3((tt * 2048 + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt,
-                                                                           reinterpret_cast<uint4*>(tx));
+  expand_pm64_kernel<<<dim3((tt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt, 1,
+                                                                                reinterpret_cast<uint4*>(tx));
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
   static bool attr_set = false;

@@ -25,6 +25,9 @@ struct SelectParams {
   const int32_t* __restrict__ t_off;
   const float2* __restrict__ kp_q;
   const float2* __restrict__ kp_t;
+  const int32_t* __restrict__ q_src;  // optional row of each pair's first keypoint (shared frames)
+  const int32_t* __restrict__ t_src;
+  int out_stride;                     // > 0: pair p's outputs start at p*out_stride, else at q_off[p]
   int32_t* __restrict__ out_q;
   int32_t* __restrict__ out_t;
   int32_t* __restrict__ out_d;
@@ -41,6 +44,7 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
   const int qo = p.q_off[pair];
   const int nq = p.q_off[pair + 1] - qo;
   const int to = p.t_off[pair];
+  const int ob = p.out_stride > 0 ? pair * p.out_stride : qo;  // output base
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (tid == 0) s_count = 0;
   __syncthreads();
@@ -95,17 +99,22 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
 
   int count = s_count;
   if (p.max_matches > 0 && count > p.max_matches) count = p.max_matches;
+  if (p.out_stride > 0 && count > p.out_stride) {  // caller's stride cannot hold this pair: flag, never overrun
+    if (tid == 0) p.out_count[pair] = -1;
+    return;
+  }
   if (tid == 0) p.out_count[pair] = count;
+  const int kq0 = p.q_src ? p.q_src[pair] : qo, kt0 = p.t_src ? p.t_src[pair] : to;
   for (int k = tid; k < count; k += nthr) {
     const uint32_t i = s_key[k] & kIdxMask;
     const uint32_t b = p.fwd_best[qo + i];
     const uint32_t j = b & kIdxMask;
-    p.out_q[qo + k] = (int32_t)i;
-    p.out_t[qo + k] = (int32_t)j;
-    p.out_d[qo + k] = (int32_t)(b >> kIdxBits);
+    p.out_q[ob + k] = (int32_t)i;
+    p.out_t[ob + k] = (int32_t)j;
+    p.out_d[ob + k] = (int32_t)(b >> kIdxBits);
     if (p.out_corr) {
-      const float2 a = p.kp_q[qo + i], c = p.kp_t[to + j];
-      p.out_corr[qo + k] = make_float4(a.x, a.y, c.x, c.y);
+      const float2 a = p.kp_q[kq0 + i], c = p.kp_t[kt0 + j];
+      p.out_corr[ob + k] = make_float4(a.x, a.y, c.x, c.y);
     }
   }
 }
@@ -116,10 +125,11 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
                                   const int32_t* q_off, const int32_t* t_off, int n_pairs, int max_nq,
                                   int use_ratio, int use_cross, const int32_t* ratio_lut_host,
                                   int sort_by_distance, int max_matches, const float* kp_q, const float* kp_t,
+                                  const int32_t* kp_q_src_row, const int32_t* kp_t_src_row, int out_stride,
                                   int32_t* out_q, int32_t* out_t, int32_t* out_d, float* out_corr,
                                   int32_t* out_count, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(n_pairs >= 0 && max_nq >= 0, "negative size");
+  B2S_REQUIRE(n_pairs >= 0 && max_nq >= 0 && out_stride >= 0, "negative size");
   B2S_REQUIRE(max_nq <= B2S_SELECT_MAX_QUERIES, "select: %d queries per pair exceeds %d", max_nq,
               B2S_SELECT_MAX_QUERIES);
   B2S_REQUIRE(!use_ratio || ratio_lut_host != nullptr, "use_ratio needs ratio_lut_host");
@@ -141,6 +151,9 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
   p.t_off = t_off;
   p.kp_q = reinterpret_cast<const float2*>(kp_q);
   p.kp_t = reinterpret_cast<const float2*>(kp_t);
+  p.q_src = kp_q_src_row;
+  p.t_src = kp_t_src_row;
+  p.out_stride = out_stride;
   p.out_q = out_q;
   p.out_t = out_t;
   p.out_d = out_d;

@@ -111,3 +111,31 @@ def test_pose_from_orb_with_inliers_identity_intrinsics():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_sequence_tracker_equals_independent_pairs():
+    """Shared-frame sequence path (frames uploaded once, q_src/t_src indirection, compact
+    outputs, 3-stream overlap) gives the same matches as independent pairs through the oracle."""
+    import torch
+    from b200slam import _capi
+    from b200slam.frontend import FrontendConfig, SequenceTracker
+    from b200slam.synthetic import tracking_sequence
+    from oracle import hamming_oracle as ho
+    F, N = 6, 700
+    desc, kp = tracking_sequence(F, N, seed=7)
+    counts = np.array([700, 650, 700, 512, 700, 699], np.int32)
+    cfg = FrontendConfig(hypotheses=128, max_matches=300)
+    for variant in (_capi.VARIANT_POPC, _capi.VARIANT_I8MMA):
+        tr = SequenceTracker(F, N, cfg, variant=variant, chunks=3)
+        out = tr.run(torch.from_numpy(desc.reshape(-1, 32)).pin_memory(), torch.from_numpy(kp.reshape(-1, 2)).pin_memory(), counts)
+        torch.cuda.synchronize()
+        for p in range(F - 1):
+            q, t = desc[p][:counts[p]], desc[p + 1][:counts[p + 1]]
+            qi, ti, d = ho.select_matches(*ho.packed_keys(q, t), use_ratio=True, use_cross=True, ratio=0.8, max_matches=300)
+            c = int(out["count"][p])
+            assert c == len(qi)
+            np.testing.assert_array_equal(out["out_q"][p * 300:p * 300 + c].numpy(), qi)
+            np.testing.assert_array_equal(out["out_t"][p * 300:p * 300 + c].numpy(), ti)
+            np.testing.assert_array_equal(out["out_d"][p * 300:p * 300 + c].numpy(), d)
+            assert int(out["best_count"][p]) == int(out["mask"][p * 300:p * 300 + c].sum())
+            assert int(out["best_count"][p]) > 0.5 * c          # the planted motion is found
