@@ -154,6 +154,13 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink,
                         void* stream);
 
+/* Raw tcgen05.mma kind::i8 rate: every SM issues iters x 8 MMAs (M=128, N=n_dim in
+ * {128,256}, K=32) from shared memory with no epilogue; *macs_out = int8 MACs issued. */
+int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream);
+/* TMEM -> register read bandwidth: every SM reads its 128 x 512 x 4 B of TMEM `iters` times
+ * with `warps` (4, 8 or 16) warps issuing tcgen05.ld 32x32b.x32; *bytes_out = bytes read. */
+int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,10 @@ def _declare(lib):
     lib.b2s_ransac_score_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, i32, vp, vp]
     lib.b2s_ransac_select.restype = i32
     lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
+    lib.b2s_mma_microbench.restype = i32
+    lib.b2s_mma_microbench.argtypes = [i32, i32, C.POINTER(dbl), vp]
+    lib.b2s_tmem_microbench.restype = i32
+    lib.b2s_tmem_microbench.argtypes = [i32, i32, C.POINTER(dbl), vp, vp]
     lib.b2s_pipe_microbench.restype = i32
     lib.b2s_pipe_microbench.argtypes = [i32, i32, i32, C.POINTER(dbl), vp, vp]
     return lib
@@ -75,7 +79,7 @@ EXPORTS = (
     "b2s_abi_version", "b2s_launch_count", "b2s_last_error", "b2s_device_info", "b2s_hamming_workspace_bytes", "b2s_hamming_workspace_bytes_v",
     "b2s_hamming_knn2_batched", "b2s_hamming_set_config", "b2s_hamming_get_config",
     "b2s_select_matches", "b2s_eight_point_batched", "b2s_ransac_score_batched",
-    "b2s_ransac_select", "b2s_pipe_microbench",
+    "b2s_ransac_select", "b2s_pipe_microbench", "b2s_mma_microbench", "b2s_tmem_microbench",
 )
 
 

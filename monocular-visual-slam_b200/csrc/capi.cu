@@ -46,6 +46,9 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
                       size_t workspace_bytes, cudaStream_t st);
 
+int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st);
+int tmem_read_launch(int iters, int warps, double* bytes_out, uint32_t* sink, cudaStream_t st);
+
 // ---- pipe microbenchmarks: 8 independent chains x 8 unrolled = 64 instructions / iteration ----
 template <int WHICH>
 __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
@@ -145,6 +148,14 @@ int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
   if (variant == B2S_VARIANT_I8MMA) return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
   return b2s_hamming_workspace_bytes(total_nq, t_split);
+}
+
+int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream) {
+  return b2s::mma_rate_launch(iters, n_dim, macs_out, static_cast<cudaStream_t>(stream));
+}
+
+int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink, void* stream) {
+  return b2s::tmem_read_launch(iters, warps, bytes_out, sink, static_cast<cudaStream_t>(stream));
 }
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {

@@ -21,9 +21,9 @@
 // Both read the same two shared-memory tiles (K-major, canonical no-swizzle core-matrix
 // layout), only the A/B descriptor roles swap.
 //
-// Pipeline (one CTA = one (pair, 128-query tile), 320 threads):
+// Pipeline (persistent CTAs, one per SM, 320 threads; work item = (pair, 128-query tile)):
 //   warp 0   producer : cp.async.bulk (TMA engine) of pre-expanded 40 KB operand tiles into
-//                       a 4-stage ring, mbarrier expect_tx / complete_tx
+//                       a 3-stage ring, mbarrier expect_tx / complete_tx
 //   warp 1   MMA      : one thread issues 18 tcgen05.mma per train tile, tcgen05.commit
 //                       releases the smem stage and publishes the TMEM accumulator stage
 //   warps 2-9 epilogue: tcgen05.ld 32x32b.x32 (thread = TMEM lane), 4-way interleaved
@@ -39,7 +39,7 @@ constexpr int kI8Chunks = 20;                     // 16-byte k-chunks per row: 1
 constexpr int kI8ChunkBytes = kI8Tile * 16;       // 2048: one k-chunk of all 128 rows (= LBO)
 constexpr int kI8TileBytes = kI8Chunks * kI8ChunkBytes;  // 40 KB
 constexpr int kI8Units = kI8Chunks * kI8Tile;     // 16-byte units per tile
-constexpr int kI8Stages = 4;
+constexpr int kI8Stages = 3;
 constexpr int kI8Threads = 320;
 constexpr int kWinBits = 13;                      // index window: 8192 rows
 constexpr int kWin = 1 << kWinBits;
@@ -156,7 +156,7 @@ struct I8Params {
   uint32_t* __restrict__ fwd_best;
   uint32_t* __restrict__ fwd_second;
   uint32_t* __restrict__ bwd_best;
-  int q_tiles, t_tiles;
+  int q_tiles, t_tiles, n_pairs;
 };
 
 // 32 accumulator columns folded into 4 interleaved top-2 chains (ILP 4; one chain would
@@ -197,26 +197,28 @@ __device__ __forceinline__ uint32_t acc_to_key(int acc, int window_base) {
   return ((u >> kWinBits) << kIdxBits) | ((u & (uint32_t)(kWin - 1)) + (uint32_t)window_base);
 }
 
+// Persistent: gridDim.x CTAs (one per SM) walk the (pair, query tile) work items round-robin.
+// TMEM, barriers and the train-tile ring are set up once; the ring and the accumulator stages
+// keep cycling across work items (global tile counter g), and the query tile is double
+// buffered, so the pipeline never drains between items.  (The first version launched one CTA
+// per item: ~36k clk per item against 19.6k clk of MMA time — prologue, first-load latency
+// and drain were un-overlapped because 200 KB of shared memory allow one CTA per SM.)
 __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_q = smem;                           // 40 KB
-  uint8_t* s_t = smem + kI8TileBytes;            // kI8Stages x 40 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kI8Stages) * kI8TileBytes);
-  uint64_t* b_full = bars;                       // [kI8Stages]
-  uint64_t* b_empty = bars + kI8Stages;          // [kI8Stages]
-  uint64_t* b_tfull = bars + 2 * kI8Stages;      // [2]
-  uint64_t* b_tempty = bars + 2 * kI8Stages + 2; // [2]
-  uint64_t* b_q = bars + 2 * kI8Stages + 4;      // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kI8Stages + 5);
-  uint2* s_merge = reinterpret_cast<uint2*>(bars + 2 * kI8Stages + 6);  // [128] fwd halves meet here
+  uint8_t* s_q = smem;                                   // 2 x 40 KB (double-buffered query tile)
+  uint8_t* s_t = smem + 2 * kI8TileBytes;                // kI8Stages x 40 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kI8Stages) * kI8TileBytes);
+  uint64_t* b_full = bars;                               // [kI8Stages]
+  uint64_t* b_empty = bars + kI8Stages;                  // [kI8Stages]
+  uint64_t* b_tfull = bars + 2 * kI8Stages;              // [2]
+  uint64_t* b_tempty = bars + 2 * kI8Stages + 2;         // [2]
+  uint64_t* b_qfull = bars + 2 * kI8Stages + 4;          // [2]
+  uint64_t* b_qempty = bars + 2 * kI8Stages + 6;         // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kI8Stages + 8);
+  uint2* s_merge = reinterpret_cast<uint2*>(bars + 2 * kI8Stages + 9);  // [128] fwd halves meet here
 
-  const int pair = blockIdx.y, qt = blockIdx.x;
-  const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
-  const int q0 = qt * kI8Tile;
-  if (q0 >= nq) return;  // CTA-uniform
-  const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
-  const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_pairs * p.q_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kI8Stages; ++s) {
@@ -226,8 +228,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     for (int a = 0; a < 2; ++a) {
       mbar_init(&b_tfull[a], 1);
       mbar_init(&b_tempty[a], 8);  // one elected arrive per epilogue warp
+      mbar_init(&b_qfull[a], 1);
+      mbar_init(&b_qempty[a], 1);
     }
-    mbar_init(b_q, 1);
     mbar_fence_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM by shared-memory footprint)
@@ -239,45 +242,68 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  // every role walks the same item sequence; items past a pair's last query tile are skipped
   if (warp == 0) {
     // ===== producer =====
     if (lane == 0) {
-      const uint8_t* qsrc = p.qx + ((size_t)pair * p.q_tiles + qt) * kI8TileBytes;
-      mbar_arrive_expect_tx(b_q, kI8TileBytes);
-      bulk_g2s(s_q, qsrc, kI8TileBytes, b_q);
-      const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
-      for (int t = 0; t < n_tt; ++t) {
-        const int s = t % kI8Stages;
-        if (t >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((uint32_t)(t / kI8Stages) - 1u) & 1u);
-        mbar_arrive_expect_tx(&b_full[s], kI8TileBytes);
-        bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, &b_full[s]);
+      uint32_t n = 0, g = 0;  // items seen by this CTA, train tiles streamed by this CTA
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
+        const int nq = p.q_off[pair + 1] - p.q_off[pair];
+        if (qt * kI8Tile >= nq) continue;
+        const int nt = p.t_off[pair + 1] - p.t_off[pair];
+        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+        const uint32_t qb = n & 1u;
+        if (n >= 2) mbar_wait_bounded(&b_qempty[qb], ((n >> 1) - 1u) & 1u);
+        mbar_arrive_expect_tx(&b_qfull[qb], kI8TileBytes);
+        bulk_g2s(s_q + (size_t)qb * kI8TileBytes, p.qx + ((size_t)pair * p.q_tiles + qt) * kI8TileBytes, kI8TileBytes,
+                 &b_qfull[qb]);
+        const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
+        for (int t = 0; t < n_tt; ++t, ++g) {
+          const uint32_t s = g % kI8Stages;
+          if (g >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((g / kI8Stages) - 1u) & 1u);
+          mbar_arrive_expect_tx(&b_full[s], kI8TileBytes);
+          bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, &b_full[s]);
+        }
+        ++n;
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      mbar_wait_bounded(b_q, 0);
-      const uint64_t qdesc = make_smem_desc(smem_u32(s_q));
-      for (int t = 0; t < n_tt; ++t) {
-        const int s = t % kI8Stages, a = t & 1;
-        if (t >= 2) mbar_wait_bounded(&b_tempty[a], ((uint32_t)(t >> 1) - 1u) & 1u);
-        mbar_wait_bounded(&b_full[s], (uint32_t)(t / kI8Stages) & 1u);
-        tc_fence_after();
-        const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
-        const uint32_t d1 = tmem_base + (uint32_t)a * 256u, d2 = d1 + 128u;
-        // K = 32 bytes per instruction = two k-chunks = 4096 B apart (descriptor units of 16 B: 256).
-        // Step 8 pairs the A tile's ones slice (chunk 16) with the B tile's index slice (chunk 18).
-        constexpr uint64_t kOnes = 16u * (kI8ChunkBytes >> 4), kIndex = 18u * (kI8ChunkBytes >> 4);
+      uint32_t n = 0, g = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
+        const int nq = p.q_off[pair + 1] - p.q_off[pair];
+        if (qt * kI8Tile >= nq) continue;
+        const int nt = p.t_off[pair + 1] - p.t_off[pair];
+        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+        const uint32_t qb = n & 1u;
+        mbar_wait_bounded(&b_qfull[qb], (n >> 1) & 1u);
+        const uint64_t qdesc = make_smem_desc(smem_u32(s_q + (size_t)qb * kI8TileBytes));
+        for (int t = 0; t < n_tt; ++t, ++g) {
+          const uint32_t s = g % kI8Stages, a = g & 1u;
+          if (g >= 2) mbar_wait_bounded(&b_tempty[a], ((g >> 1) - 1u) & 1u);
+          mbar_wait_bounded(&b_full[s], (g / kI8Stages) & 1u);
+          tc_fence_after();
+          const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
+          const uint32_t d1 = tmem_base + a * 256u, d2 = d1 + 128u;
+          // K = 32 bytes per instruction = two k-chunks = 4096 B apart (descriptor units of 16 B: 256).
+          // Step 8 pairs the A tile's ones slice (chunk 16) with the B tile's index slice (chunk 18).
+          constexpr uint64_t kOnes = 16u * (kI8ChunkBytes >> 4), kIndex = 18u * (kI8ChunkBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          tc_mma_i8(d1, qdesc + (uint64_t)k * 256u, tdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
-        tc_mma_i8(d1, qdesc + kOnes, tdesc + kIndex, kIdescI8, 1);
+          for (int k = 0; k < 8; ++k)
+            tc_mma_i8(d1, qdesc + (uint64_t)k * 256u, tdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+          tc_mma_i8(d1, qdesc + kOnes, tdesc + kIndex, kIdescI8, 1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          tc_mma_i8(d2, tdesc + (uint64_t)k * 256u, qdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
-        tc_mma_i8(d2, tdesc + kOnes, qdesc + kIndex, kIdescI8, 1);
-        tc_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
-        tc_commit(&b_tfull[a]);  // accumulators complete
+          for (int k = 0; k < 8; ++k)
+            tc_mma_i8(d2, tdesc + (uint64_t)k * 256u, qdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
+          tc_mma_i8(d2, tdesc + kOnes, qdesc + kIndex, kIdescI8, 1);
+          tc_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
+          tc_commit(&b_tfull[a]);  // accumulators complete
+        }
+        tc_commit(&b_qempty[qb]);  // query tile buffer reusable once this item's MMAs have read it
+        ++n;
       }
     }
   } else {
@@ -286,68 +312,78 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;  // TMEM lane = tile row
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int nq_valid = min(kI8Tile, nq - q0);
-    uint32_t gbest = kNone, gsecond = kNone;
-    int b[4] = {kAccNone, kAccNone, kAccNone, kAccNone}, s2[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
-    const int q_window = q0 & ~(kWin - 1);
-    for (int t = 0; t < n_tt; ++t) {
-      const int a = t & 1;
-      const int tbase = t * kI8Tile;
-      const int nt_valid = min(kI8Tile, nt - tbase);
-      mbar_wait_bounded(&b_tfull[a], (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      // ---- D1: this thread's query row vs 64 train columns ----
-      const uint32_t c1 = lane_addr + (uint32_t)a * 256u + (uint32_t)half * 64u;
-      TMEM_LD_X32(c1, v0);
-      TMEM_LD_X32(c1 + 32u, v1);
-      tmem_ld_wait();
-      if (nt_valid == kI8Tile) {
-        fold_top2<false>(v0, half * 64, kI8Tile, b, s2);
-        fold_top2<false>(v1, half * 64 + 32, kI8Tile, b, s2);
-      } else {
-        fold_top2<true>(v0, half * 64, nt_valid, b, s2);
-        fold_top2<true>(v1, half * 64 + 32, nt_valid, b, s2);
-      }
-      // ---- D2: this thread's train row vs 64 query columns ----
-      const uint32_t c2 = c1 + 128u;
-      TMEM_LD_X32(c2, v0);
-      TMEM_LD_X32(c2 + 32u, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&b_tempty[a]);  // accumulator stage drained into registers
-      int m[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
-      if (nq_valid == kI8Tile) {
-        fold_min<false>(v0, half * 64, kI8Tile, m);
-        fold_min<false>(v1, half * 64 + 32, kI8Tile, m);
-      } else {
-        fold_min<true>(v0, half * 64, nq_valid, m);
-        fold_min<true>(v1, half * 64 + 32, nq_valid, m);
-      }
-      const int cm = min(min(m[0], m[1]), min(m[2], m[3]));
-      if (row < nt_valid && cm != kAccNone) atomicMin(&p.bwd_best[to + tbase + row], acc_to_key(cm, q_window));
-      // leave the accumulator domain when the train index window (8192 rows) ends
-      if (((t + 1) & (kWin / kI8Tile - 1)) == 0 || t == n_tt - 1) {
-        const int window_base = tbase & ~(kWin - 1);
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
+      const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
+      const int q0 = qt * kI8Tile;
+      if (q0 >= nq) continue;
+      const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
+      const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+      const int nq_valid = min(kI8Tile, nq - q0);
+      uint32_t gbest = kNone, gsecond = kNone;
+      int b[4] = {kAccNone, kAccNone, kAccNone, kAccNone}, s2[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
+      const int q_window = q0 & ~(kWin - 1);
+      for (int t = 0; t < n_tt; ++t, ++g) {
+        const uint32_t a = g & 1u;
+        const int tbase = t * kI8Tile;
+        const int nt_valid = min(kI8Tile, nt - tbase);
+        mbar_wait_bounded(&b_tfull[a], (g >> 1) & 1u);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        // ---- D1: this thread's query row vs 64 train columns ----
+        const uint32_t c1 = lane_addr + a * 256u + (uint32_t)half * 64u;
+        TMEM_LD_X32(c1, v0);
+        TMEM_LD_X32(c1 + 32u, v1);
+        tmem_ld_wait();
+        if (nt_valid == kI8Tile) {
+          fold_top2<false>(v0, half * 64, kI8Tile, b, s2);
+          fold_top2<false>(v1, half * 64 + 32, kI8Tile, b, s2);
+        } else {
+          fold_top2<true>(v0, half * 64, nt_valid, b, s2);
+          fold_top2<true>(v1, half * 64 + 32, nt_valid, b, s2);
+        }
+        // ---- D2: this thread's train row vs 64 query columns ----
+        const uint32_t c2 = c1 + 128u;
+        TMEM_LD_X32(c2, v0);
+        TMEM_LD_X32(c2 + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_tempty[a]);  // accumulator stage drained into registers
+        int m[4] = {kAccNone, kAccNone, kAccNone, kAccNone};
+        if (nq_valid == kI8Tile) {
+          fold_min<false>(v0, half * 64, kI8Tile, m);
+          fold_min<false>(v1, half * 64 + 32, kI8Tile, m);
+        } else {
+          fold_min<true>(v0, half * 64, nq_valid, m);
+          fold_min<true>(v1, half * 64 + 32, nq_valid, m);
+        }
+        const int cm = min(min(m[0], m[1]), min(m[2], m[3]));
+        if (row < nt_valid && cm != kAccNone) atomicMin(&p.bwd_best[to + tbase + row], acc_to_key(cm, q_window));
+        // leave the accumulator domain when the train index window (8192 rows) ends
+        if (((t + 1) & (kWin / kI8Tile - 1)) == 0 || t == n_tt - 1) {
+          const int window_base = tbase & ~(kWin - 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (b[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(b[k], window_base));
-          if (s2[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(s2[k], window_base));
-          b[k] = kAccNone;
-          s2[k] = kAccNone;
+          for (int k = 0; k < 4; ++k) {
+            if (b[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(b[k], window_base));
+            if (s2[k] != kAccNone) top2_insert(gbest, gsecond, acc_to_key(s2[k], window_base));
+            b[k] = kAccNone;
+            s2[k] = kAccNone;
+          }
         }
       }
-    }
-    // the two column halves of a query row meet in shared memory
-    if (half == 1) s_merge[row] = make_uint2(gbest, gsecond);
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
-    if (half == 0 && row < nq_valid) {
-      const uint2 o = s_merge[row];
-      top2_insert(gbest, gsecond, o.x);
-      top2_insert(gbest, gsecond, o.y);
-      p.fwd_best[qo + q0 + row] = gbest;
-      p.fwd_second[qo + q0 + row] = gsecond;
+      // the two column halves of a query row meet in shared memory
+      if (half == 1) s_merge[row] = make_uint2(gbest, gsecond);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      if (half == 0 && row < nq_valid) {
+        const uint2 o = s_merge[row];
+        top2_insert(gbest, gsecond, o.x);
+        top2_insert(gbest, gsecond, o.y);
+        p.fwd_best[qo + q0 + row] = gbest;
+        p.fwd_second[qo + q0 + row] = gsecond;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_merge free for the next item
     }
   }
 
@@ -359,7 +395,106 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
   }
 }
 
-constexpr size_t kI8SmemBytes = (size_t)(1 + kI8Stages) * kI8TileBytes + 8 * (2 * kI8Stages + 6) + 128 * sizeof(uint2);
+// ---- measurement: raw tcgen05.mma kind::i8 issue rate (no epilogue), one CTA per SM ------
+// n_dim = 128 or 256; A = 128 rows, B = n_dim rows, both in the canonical no-swizzle layout.
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n_dim) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (3 * kI8TileBytes) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tm)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s_tm;
+  if (warp == 1 && lane == 0) {
+    const uint64_t adesc = make_smem_desc(smem_u32(smem));
+    const uint64_t bdesc = make_smem_desc(smem_u32(smem + kI8TileBytes));
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)n_dim >> 3) << 17) | ((128u >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tm + (uint32_t)((it & 1) * 256);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tc_mma_i8(d, adesc + (uint64_t)k * 256u, bdesc + (uint64_t)k * 256u, idesc, k > 0);
+    }
+    tc_commit(&bar);
+    mbar_wait_bounded(&bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+  }
+}
+
+// ---- measurement: TMEM -> register read bandwidth (tcgen05.ld 32x32b.x32), `warps` warps per SM
+__global__ void __launch_bounds__(512, 1) tmem_read_kernel(int iters, uint32_t* sink) {
+  __shared__ uint32_t s_tm;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tm)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s_tm;
+  const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16);
+  const int nw = blockDim.x >> 5;
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    // the warps sharing a lane quarter split the 512 columns
+    const int per = 512 / (nw / 4);
+    const int c0 = (warp >> 2) * per;
+    for (int c = c0; c < c0 + per; c += 64) {
+      uint32_t v0[32], v1[32];
+      TMEM_LD_X32(lane_addr + (uint32_t)c, v0);
+      TMEM_LD_X32(lane_addr + (uint32_t)c + 32u, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; k += 8) acc ^= v0[k] ^ v1[k];
+    }
+  }
+  if (acc == 0x12345u) sink[0] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+  }
+}
+
+int tmem_read_launch(int iters, int warps, double* bytes_out, uint32_t* sink, cudaStream_t st) {
+  B2S_REQUIRE(warps == 4 || warps == 8 || warps == 16, "warps must be 4, 8 or 16");
+  tmem_read_kernel<<<sm_count(), warps * 32, 0, st>>>(iters, sink);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  if (bytes_out) *bytes_out = (double)sm_count() * iters * 128.0 * 512.0 * 4.0;
+  return B2S_OK;
+}
+
+int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st) {
+  B2S_REQUIRE(n_dim == 128 || n_dim == 256, "n_dim must be 128 or 256");
+  const size_t smem = 3 * (size_t)kI8TileBytes;
+  B2S_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate_kernel<<<sm_count(), 128, smem, st>>>(iters, n_dim);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  if (macs_out) *macs_out = (double)sm_count() * iters * 8.0 * 128.0 * n_dim * 32.0;
+  return B2S_OK;
+}
+
+constexpr size_t kI8SmemBytes = (size_t)(2 + kI8Stages) * kI8TileBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
@@ -407,7 +542,10 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.bwd_best = bwd_best;
   p.q_tiles = qt;
   p.t_tiles = tt;
-  hamming_knn2_i8_kernel<<<dim3(qt, n_pairs), kI8Threads, kI8SmemBytes, st>>>(p);
+  p.n_pairs = n_pairs;
+  const long items = (long)qt * n_pairs;
+  const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
+  hamming_knn2_i8_kernel<<<grid, kI8Threads, kI8SmemBytes, st>>>(p);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;
