@@ -160,6 +160,7 @@ def b200_main(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2S_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     lib = _capi.load_library()
@@ -238,6 +239,28 @@ def b200_main(a):
     popc_ops = 8.0 * float(a.pairs) * a.nfeat * a.nfeat                    # algorithmic POPC32 per launch
     alg_bytes = float(batch.total_nq + batch.total_nt) * 32 + 4.0 * (2 * batch.total_nq + batch.total_nt)
 
+    # ---- per-stage device times (CUDA events around each C-ABI call, same inputs) ----
+    def stage_times(reps=5):
+        c = fe.cfg
+        acc = {}
+        def tm(name, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            e1.synchronize()
+            acc.setdefault(name, []).append(e0.elapsed_time(e1))
+            return out
+        for _ in range(reps + 1):
+            keys = tm("hamming", lambda: fe.matcher.knn2(batch))
+            sel = tm("select", lambda: fe.matcher.select(batch, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
+                                                         sort_by_distance=True, max_matches=c.max_matches, with_corr=True, compact=True))
+            E = tm("eight_point", lambda: fe.ransac.hypotheses(sel.corr, sel.c_off, sel.count, batch.n_pairs, c.hypotheses, seed=c.seed))
+            cnts = tm("score", lambda: fe.ransac.score(sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2, precision=c.precision))
+            tm("winner", lambda: fe.ransac.select(cnts, sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2))
+        return {k: float(np.mean(v[1:])) for k, v in acc.items()}
+    stages = stage_times()
+
     # ---- end to end through host buffers: pinned host frames -> device -> kernels -> pinned host ----
     tracker = SequenceTracker(a.pairs + 1, a.nfeat, cfg, variant=variant, chunks=a.chunks, device=dev)
     tracker.fe = fe
@@ -304,7 +327,7 @@ def b200_main(a):
             "clocks": clk, "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": len(tracker.bounds),
                     "ms_per_step": e2e_total / a.steps},
-            "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
+            "stage_ms": stages, "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
             "kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
     if a.sweep:
         line["popc_kernel_sweep_ms"] = sweep(lib, fe, batch, timed, a)

@@ -154,6 +154,12 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink,
                         void* stream);
 
+/* Diagnostics: when dev_buf != NULL (device memory, 8 x uint64 per SM) the i8 Hamming kernel
+ * records, per CTA, clock64 totals: [0] MMA thread total, [1] MMA waiting for a free TMEM stage,
+ * [2] MMA waiting for operand tiles, [3] producer waiting for a free ring slot, [4] epilogue
+ * warp total, [5] epilogue waiting for accumulators, [6] tile pairs.  NULL switches it off. */
+void b2s_hamming_i8_debug(unsigned long long* dev_buf);
+
 /* Raw tcgen05.mma kind::i8 rate: every SM issues iters x 8 MMAs (M=128, N=n_dim in
  * {128,256}, K=32) from shared memory with no epilogue; *macs_out = int8 MACs issued. */
 int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream);

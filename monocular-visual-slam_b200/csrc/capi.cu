@@ -46,6 +46,7 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
                       size_t workspace_bytes, cudaStream_t st);
 
+void hamming_i8_set_debug(unsigned long long* dev_buf);
 int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st);
 int tmem_read_launch(int iters, int warps, double* bytes_out, uint32_t* sink, cudaStream_t st);
 
@@ -149,6 +150,8 @@ size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int
   if (variant == B2S_VARIANT_I8MMA) return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
   return b2s_hamming_workspace_bytes(total_nq, t_split);
 }
+
+void b2s_hamming_i8_debug(unsigned long long* dev_buf) { b2s::hamming_i8_set_debug(dev_buf); }
 
 int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream) {
   return b2s::mma_rate_launch(iters, n_dim, macs_out, static_cast<cudaStream_t>(stream));

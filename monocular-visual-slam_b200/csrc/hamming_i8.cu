@@ -157,7 +157,10 @@ struct I8Params {
   uint32_t* __restrict__ fwd_second;
   uint32_t* __restrict__ bwd_best;
   int q_tiles, t_tiles, n_pairs;
+  unsigned long long* dbg;  // optional per-CTA stall counters (b2s_hamming_i8_debug), else nullptr
 };
+// dbg layout per CTA (8 x u64): [0] MMA thread total, [1] MMA wait tempty, [2] MMA wait full/qfull,
+// [3] producer wait empty, [4] epilogue warp 2 total, [5] epilogue wait tfull, [6] tile pairs, [7] -
 
 // 32 accumulator columns folded into 4 interleaved top-2 chains (ILP 4; one chain would
 // serialise on the 4-cycle ALU latency).  Two columns per step: the two smallest of
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     // ===== producer =====
     if (lane == 0) {
       uint32_t n = 0, g = 0;  // items seen by this CTA, train tiles streamed by this CTA
+      long long w_empty = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
         const int nq = p.q_off[pair + 1] - p.q_off[pair];
@@ -261,17 +265,22 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
         for (int t = 0; t < n_tt; ++t, ++g) {
           const uint32_t s = g % kI8Stages;
+          const long long c0 = p.dbg ? clock64() : 0;
           if (g >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((g / kI8Stages) - 1u) & 1u);
+          if (p.dbg) w_empty += clock64() - c0;
           mbar_arrive_expect_tx(&b_full[s], kI8TileBytes);
           bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, &b_full[s]);
         }
         ++n;
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t n = 0, g = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_start = p.dbg ? clock64() : 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
         const int nq = p.q_off[pair + 1] - p.q_off[pair];
@@ -279,12 +288,20 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         const int nt = p.t_off[pair + 1] - p.t_off[pair];
         const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
         const uint32_t qb = n & 1u;
+        long long c0 = p.dbg ? clock64() : 0;
         mbar_wait_bounded(&b_qfull[qb], (n >> 1) & 1u);
+        if (p.dbg) w_full += clock64() - c0;
         const uint64_t qdesc = make_smem_desc(smem_u32(s_q + (size_t)qb * kI8TileBytes));
         for (int t = 0; t < n_tt; ++t, ++g) {
           const uint32_t s = g % kI8Stages, a = g & 1u;
+          c0 = p.dbg ? clock64() : 0;
           if (g >= 2) mbar_wait_bounded(&b_tempty[a], ((g >> 1) - 1u) & 1u);
+          long long c1 = p.dbg ? clock64() : 0;
           mbar_wait_bounded(&b_full[s], (g / kI8Stages) & 1u);
+          if (p.dbg) {
+            w_tempty += c1 - c0;
+            w_full += clock64() - c1;
+          }
           tc_fence_after();
           const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
           const uint32_t d1 = tmem_base + a * 256u, d2 = d1 + 128u;
@@ -305,6 +322,12 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         tc_commit(&b_qempty[qb]);  // query tile buffer reusable once this item's MMAs have read it
         ++n;
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_start);
+        p.dbg[blockIdx.x * 8 + 1] = (unsigned long long)w_tempty;
+        p.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full;
+        p.dbg[blockIdx.x * 8 + 6] = g;
+      }
     }
   } else {
     // ===== epilogue: 8 warps; warp%4 = TMEM lane quarter, (warp-2)/4 = column half =====
@@ -313,6 +336,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     const int row = quarter * 32 + lane;  // TMEM lane = tile row
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t g = 0;
+    long long w_tfull = 0;
+    const long long e_start = p.dbg ? clock64() : 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int pair = w / p.q_tiles, qt = w - pair * p.q_tiles;
       const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
@@ -328,7 +353,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         const uint32_t a = g & 1u;
         const int tbase = t * kI8Tile;
         const int nt_valid = min(kI8Tile, nt - tbase);
+        const long long c0 = p.dbg ? clock64() : 0;
         mbar_wait_bounded(&b_tfull[a], (g >> 1) & 1u);
+        if (p.dbg) w_tfull += clock64() - c0;
         tc_fence_after();
         uint32_t v0[32], v1[32];
         // ---- D1: this thread's query row vs 64 train columns ----
@@ -384,6 +411,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         p.fwd_second[qo + q0 + row] = gsecond;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // s_merge free for the next item
+    }
+    if (p.dbg && threadIdx.x == 64) {
+      p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
+      p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
     }
   }
 
@@ -494,6 +525,9 @@ int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st) {
   return B2S_OK;
 }
 
+static unsigned long long* g_i8_dbg = nullptr;  // device buffer, 8 u64 per SM (diagnostics only)
+void hamming_i8_set_debug(unsigned long long* dev_buf) { g_i8_dbg = dev_buf; }
+
 constexpr size_t kI8SmemBytes = (size_t)(2 + kI8Stages) * kI8TileBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
@@ -543,6 +577,7 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.q_tiles = qt;
   p.t_tiles = tt;
   p.n_pairs = n_pairs;
+  p.dbg = g_i8_dbg;
   const long items = (long)qt * n_pairs;
   const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
   hamming_knn2_i8_kernel<<<grid, kI8Threads, kI8SmemBytes, st>>>(p);

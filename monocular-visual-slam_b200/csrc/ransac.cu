@@ -142,86 +142,72 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-// Null vector of an 8x9 matrix: Gaussian elimination with complete pivoting + back
-// substitution.  The matrix lives in shared memory, element-major ([r*9+c][thread]), so
-// the dynamically indexed accesses complete pivoting needs are bank-conflict free and
-// never touch local memory (the first version kept A in local memory and was 12x off the
-// FP64 pipe bound, stalled on long-scoreboard).
-constexpr int kEpThreads = 64;
-#define A_(r, c) sA[((r) * 9 + (c)) * kEpThreads]
+// Null vector of an 8x9 matrix, entirely in registers with static indexing.
+// Gaussian elimination with the pivot ROW fixed (row k at step k) and the pivot COLUMN chosen
+// as the largest remaining entry of that row (= partial pivoting on A^T).  Nothing is ever
+// swapped: used columns are a bit mask, a dynamically chosen column is read with a 9-way
+// select chain, and the free (never chosen) column takes the value 1 in the back
+// substitution.  Adaptive columns matter here: for forward motion E33 ~ 0, so fixing the
+// last column as the free one would make the 8x8 system singular.
+// History: matrix in local memory 947 us -> shared memory + complete pivoting 386 us
+// (10.5k instructions per hypothesis, latency bound) -> this version.
+constexpr int kEpThreads = 128;
 
-__device__ void null_vector_8x9(double* sA /* already offset by threadIdx.x */, double* v) {
-  uint64_t perm = 0x876543210ull;  // column permutation, one nibble per column (stays in registers)
-  int rank = 8;
+__device__ __forceinline__ double pick9(const double (&a)[9], int c) {
+  double v = a[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) v = (c == i) ? a[i] : v;
+  return v;
+}
+
+__device__ __forceinline__ void null_vector_8x9(double (&A)[8][9], double (&v)[9]) {
+  unsigned used = 0u;
+  int pcs[8];
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
-    int pr = k, pc = k;
-    double big = 0.0;
-    for (int r = k; r < 8; ++r)
-      for (int c = k; c < 9; ++c) {
-        const double a = fabs(A_(r, c));
-        if (a > big) {
-          big = a;
-          pr = r;
-          pc = c;
-        }
-      }
-    if (big == 0.0) {
-      rank = k;
-      break;
-    }
-    if (pc != k) {  // column swap touches every row (back substitution reads the upper part)
-      for (int r = 0; r < 8; ++r) {
-        const double tmp = A_(r, k);
-        A_(r, k) = A_(r, pc);
-        A_(r, pc) = tmp;
-      }
-      const uint64_t a = (perm >> (4 * k)) & 15ull, b = (perm >> (4 * pc)) & 15ull;
-      perm ^= ((a ^ b) << (4 * k)) | ((a ^ b) << (4 * pc));
-    }
-    double prow[9];  // pivot row (columns k..8), swapped into place on the fly
-    double piv = 1.0;
+    int pc = 0;
+    double big = -1.0;
 #pragma unroll
     for (int c = 0; c < 9; ++c) {
-      if (c >= k) {
-        prow[c] = A_(pr, c);
-        if (pr != k) {
-          A_(pr, c) = A_(k, c);
-          A_(k, c) = prow[c];
-        }
-        if (c == k) piv = prow[c];
+      const double a = ((used >> c) & 1u) ? -1.0 : fabs(A[k][c]);
+      if (a > big) {
+        big = a;
+        pc = c;
       }
     }
-    const double inv = 1.0 / piv;
-    for (int r = k + 1; r < 8; ++r) {
-      const double f = A_(r, k) * inv;
+    used |= 1u << pc;
+    pcs[k] = pc;
+    const double inv = (big > 0.0) ? 1.0 / pick9(A[k], pc) : 0.0;
 #pragma unroll
-      for (int c = 0; c < 9; ++c)
-        if (c > k) A_(r, c) = fma(-f, prow[c], A_(r, c));
+    for (int r = k + 1; r < 8; ++r) {
+      const double f = pick9(A[r], pc) * inv;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) A[r][c] = fma(-f, A[k][c], A[r][c]);
     }
   }
-  // back substitution in permuted column order: x[8] = 1, free x[rank..7] = 0
+  int fc = 0;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) fc = ((used >> c) & 1u) ? fc : c;
   double x[9];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) x[c] = (c == 8) ? 1.0 : 0.0;
+  for (int c = 0; c < 9; ++c) x[c] = (c == fc) ? 1.0 : 0.0;
 #pragma unroll
   for (int k = 7; k >= 0; --k) {
-    if (k < rank) {
-      double acc = 0.0;
+    // x of this row's pivot column is still 0 and columns eliminated earlier multiply x = 0
+    double acc = 0.0;
 #pragma unroll
-      for (int c = 0; c < 9; ++c)
-        if (c > k) acc = fma(A_(k, c), x[c], acc);
-      x[k] = -acc / A_(k, k);
-    }
+    for (int c = 0; c < 9; ++c) acc = fma(A[k][c], x[c], acc);
+    const double piv = pick9(A[k], pcs[k]);
+    const double val = (piv != 0.0) ? -acc / piv : 0.0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) x[c] = (c == pcs[k]) ? val : x[c];
   }
   double n2 = 0.0;
 #pragma unroll
   for (int c = 0; c < 9; ++c) n2 = fma(x[c], x[c], n2);
   const double sc = rsqrt(n2);
-  // un-permute through shared memory (row 0 is dead now) to avoid a dynamically indexed local array
 #pragma unroll
-  for (int c = 0; c < 9; ++c) A_(0, (int)((perm >> (4 * c)) & 15ull)) = x[c] * sc;
-#pragma unroll
-  for (int c = 0; c < 9; ++c) v[c] = A_(0, c);
+  for (int c = 0; c < 9; ++c) v[c] = x[c] * sc;
 }
 
 // Smallest-eigenvalue eigenvector of the symmetric 3x3 S (cyclic Jacobi).
@@ -267,7 +253,6 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count, int H,
     const int32_t* __restrict__ samples_in, uint64_t seed, int32_t* __restrict__ samples_out, const Mat3 K,
     const Mat3 Kinv, double* __restrict__ E_out) {
-  __shared__ double s_A[72 * kEpThreads];  // 36 KB: one 8x9 system per thread, element-major
   const int pair = blockIdx.y;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
@@ -301,7 +286,8 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     return;
   }
 
-  double* sA = &s_A[threadIdx.x];
+  double A[8][9];
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float4 c = cp[idx[k]];
     const double sx = c.x, sy = c.y, dx = c.z, dy = c.w;
@@ -313,12 +299,12 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     const double w2 = fma(ki[6], dx, fma(ki[7], dy, ki[8]));
     const double u = fma(ki[0], dx, fma(ki[1], dy, ki[2])) / w2;
     const double v = fma(ki[3], dx, fma(ki[4], dy, ki[5])) / w2;
-    A_(k, 0) = u * x; A_(k, 1) = u * y; A_(k, 2) = u;
-    A_(k, 3) = v * x; A_(k, 4) = v * y; A_(k, 5) = v;
-    A_(k, 6) = x;     A_(k, 7) = y;     A_(k, 8) = 1.0;
+    A[k][0] = u * x; A[k][1] = u * y; A[k][2] = u;
+    A[k][3] = v * x; A[k][4] = v * y; A[k][5] = v;
+    A[k][6] = x;     A[k][7] = y;     A[k][8] = 1.0;
   }
   double f[9];
-  null_vector_8x9(sA, f);
+  null_vector_8x9(A, f);
 
   // rank-2 projection: F' = F - (F v3) v3^T, v3 = right-singular vector of the smallest
   // singular value (homography.py:244-246 zeroes S[2] only).

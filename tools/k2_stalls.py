@@ -1,0 +1,46 @@
+"""Diagnostics (GPU): where the i8 Hamming kernel's MMA thread / producer / epilogue wait.
+Usage: python tools/k2_stalls.py [pairs] [nfeat]"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "monocular-visual-slam_b200")]
+import ctypes as C
+
+import numpy as np
+import torch
+
+from b200slam import _capi
+from b200slam.frontend import HammingMatcher, PairBatch
+
+pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+lib = _capi.load_library()
+rng = np.random.default_rng(0)
+qs = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(pairs)]
+ts = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(pairs)]
+batch = PairBatch.from_host(qs, ts)
+m = HammingMatcher(variant=_capi.VARIANT_I8MMA)
+for _ in range(3):
+    m.knn2(batch)
+torch.cuda.synchronize()
+# MMA issue-rate microbenchmark, N = 128 and 256
+for nd in (128, 256):
+    macs = C.c_double()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.b2s_mma_microbench(2000, nd, C.byref(macs), None)
+    torch.cuda.synchronize()
+    e0.record(); lib.b2s_mma_microbench(2000, nd, C.byref(macs), None); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"mma N={nd}: {2*macs.value/ms/1e12:.1f} TOP/s, {ms*1e-3*1.965e9/(2000*8):.1f} clk/instr")
+dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+lib.b2s_hamming_i8_debug(C.c_void_p(dbg.data_ptr()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); m.knn2(batch); e1.record(); torch.cuda.synchronize()
+lib.b2s_hamming_i8_debug(None)
+d = dbg.cpu().numpy().reshape(148, 8).astype(np.float64)
+tp = d[:, 6]
+print(f"knn2 call {e0.elapsed_time(e1):.3f} ms; tile pairs/CTA mean {tp.mean():.0f}")
+names = ["mma_total", "mma_wait_tempty", "mma_wait_full", "prod_wait_empty", "epi_total", "epi_wait_tfull"]
+for i, nm in enumerate(names):
+    print(f"{nm:18s} mean {d[:, i].mean():12.0f} clk  per tile pair {d[:, i].sum() / tp.sum():8.1f}")
