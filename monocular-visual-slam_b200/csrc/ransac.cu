@@ -142,113 +142,110 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-// Null vector of an 8x9 matrix, entirely in registers with static indexing.
-// Gaussian elimination with the pivot ROW fixed (row k at step k) and the pivot COLUMN chosen
-// as the largest remaining entry of that row (= partial pivoting on A^T).  Nothing is ever
-// swapped: used columns are a bit mask, a dynamically chosen column is read with a 9-way
-// select chain, and the free (never chosen) column takes the value 1 in the back
-// substitution.  Adaptive columns matter here: for forward motion E33 ~ 0, so fixing the
-// last column as the free one would make the 8x8 system singular.
-// History: matrix in local memory 947 us -> shared memory + complete pivoting 386 us
-// (10.5k instructions per hypothesis, latency bound) -> this version.
+// Null vector of the 8x9 design matrix A: Householder QR of A^T (9x8, one column per sampled
+// correspondence); the last column of Q = H0 H1 ... H7 spans the orthogonal complement of the
+// rows of A.  Everything is statically indexed (registers only), there is no pivot search and no
+// select chain, and no column has to be singled out as the "free" one (for forward motion
+// E33 ~ 0, so a fixed free column would make the 8x8 system singular).  The reflector tails
+// overwrite the entries they annihilate (LAPACK storage), so the whole solve lives in the 72
+// registers of A plus 16 scalars.  The result has unit norm by construction.
+// History (us per 592k hypotheses): matrix in local memory 947 -> shared memory + complete
+// pivoting 386 -> registers + row-fixed column pivoting (select chains, 7.3k instructions per
+// hypothesis) 328 -> this version.
 constexpr int kEpThreads = 128;
 
-__device__ __forceinline__ double pick9(const double (&a)[9], int c) {
-  double v = a[0];
-#pragma unroll
-  for (int i = 1; i < 9; ++i) v = (c == i) ? a[i] : v;
-  return v;
-}
-
-__device__ __forceinline__ void null_vector_8x9(double (&A)[8][9], double (&v)[9]) {
-  unsigned used = 0u;
-  int pcs[8];
+__device__ __forceinline__ void null_vector_8x9(double (&A)[8][9], double (&n)[9]) {
+  double v0[8], beta[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    int pc = 0;
-    double big = -1.0;
+    // column k of A^T below the diagonal = A[k][k..8]
+    double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      const double a = ((used >> c) & 1u) ? -1.0 : fabs(A[k][c]);
-      if (a > big) {
-        big = a;
-        pc = c;
-      }
-    }
-    used |= 1u << pc;
-    pcs[k] = pc;
-    const double inv = (big > 0.0) ? 1.0 / pick9(A[k], pc) : 0.0;
+    for (int i = k; i < 9; ++i) s = fma(A[k][i], A[k][i], s);
+    const double nrm = s * rsqrt(s);                 // sqrt(s); NaN for s = 0, masked by beta below
+    const double x0 = A[k][k];
+    v0[k] = x0 + copysign(nrm, x0);
+    beta[k] = (s > 0.0) ? 1.0 / fma(fabs(x0), nrm, s) : 0.0;  // 2 / (v^T v)
+    if (!(s > 0.0)) v0[k] = 0.0;
 #pragma unroll
-    for (int r = k + 1; r < 8; ++r) {
-      const double f = pick9(A[r], pc) * inv;
+    for (int j = k + 1; j < 8; ++j) {
+      double d = v0[k] * A[j][k];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) A[r][c] = fma(-f, A[k][c], A[r][c]);
+      for (int i = k + 1; i < 9; ++i) d = fma(A[k][i], A[j][i], d);
+      d *= beta[k];
+      A[j][k] = fma(-d, v0[k], A[j][k]);
+#pragma unroll
+      for (int i = k + 1; i < 9; ++i) A[j][i] = fma(-d, A[k][i], A[j][i]);
     }
   }
-  int fc = 0;
 #pragma unroll
-  for (int c = 0; c < 9; ++c) fc = ((used >> c) & 1u) ? fc : c;
-  double x[9];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) x[c] = (c == fc) ? 1.0 : 0.0;
+  for (int i = 0; i < 9; ++i) n[i] = (i == 8) ? 1.0 : 0.0;
 #pragma unroll
   for (int k = 7; k >= 0; --k) {
-    // x of this row's pivot column is still 0 and columns eliminated earlier multiply x = 0
-    double acc = 0.0;
+    double d = v0[k] * n[k];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) acc = fma(A[k][c], x[c], acc);
-    const double piv = pick9(A[k], pcs[k]);
-    const double val = (piv != 0.0) ? -acc / piv : 0.0;
+    for (int i = k + 1; i < 9; ++i) d = fma(A[k][i], n[i], d);
+    d *= beta[k];
+    n[k] = fma(-d, v0[k], n[k]);
 #pragma unroll
-    for (int c = 0; c < 9; ++c) x[c] = (c == pcs[k]) ? val : x[c];
+    for (int i = k + 1; i < 9; ++i) n[i] = fma(-d, A[k][i], n[i]);
   }
-  double n2 = 0.0;
-#pragma unroll
-  for (int c = 0; c < 9; ++c) n2 = fma(x[c], x[c], n2);
-  const double sc = rsqrt(n2);
-#pragma unroll
-  for (int c = 0; c < 9; ++c) v[c] = x[c] * sc;
 }
 
-// Smallest-eigenvalue eigenvector of the symmetric 3x3 S (cyclic Jacobi).
-__device__ void smallest_eigvec3(double S[3][3], double* out) {
-  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int sweep = 0; sweep < 8; ++sweep) {
-    const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
-    if (off == 0.0) break;
+// Right-singular vector of the smallest singular value of the 3x3 matrix f (row-major).
+// cof(F) = s2 s3 u1 v1^T + s1 s3 u2 v2^T + s1 s2 u3 v3^T, so v3 is the DOMINANT eigenvector of
+// M = cof(F)^T cof(F) with eigenvalue ratio (s3/s2)^2; repeated squaring of the trace-normalised
+// M squares that ratio every step.  With tr(M) = 1 the trace of M^2 is 1 - 2*delta (delta = the
+// second eigenvalue), so the loop stops after the squaring that saw delta < 1e-8: its result is
+// rank one to 1e-16.  3-6 squarings for well-posed samples, 12+ only when s3/s2 > 0.99.
+// No division, square root or trigonometry inside the loop (the cyclic Jacobi solver this
+// replaces spent ~5k instructions per hypothesis on them).
+__device__ __forceinline__ void smallest_right_singular3(const double (&f)[9], double (&v)[3]) {
+  double c[9];
 #pragma unroll
-    for (int pq = 0; pq < 3; ++pq) {
-      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
-      const double apq = S[p][q];
-      if (apq == 0.0) continue;
-      const double theta = (S[q][q] - S[p][p]) / (2.0 * apq);
-      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-      const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
-      for (int k = 0; k < 3; ++k) {  // S <- S J
-        const double skp = S[k][p], skq = S[k][q];
-        S[k][p] = c * skp - s * skq;
-        S[k][q] = s * skp + c * skq;
-      }
-      for (int k = 0; k < 3; ++k) {  // S <- J^T S
-        const double spk = S[p][k], sqk = S[q][k];
-        S[p][k] = c * spk - s * sqk;
-        S[q][k] = s * spk + c * sqk;
-      }
-      for (int k = 0; k < 3; ++k) {
-        const double vkp = V[k][p], vkq = V[k][q];
-        V[k][p] = c * vkp - s * vkq;
-        V[k][q] = s * vkp + c * vkq;
-      }
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      c[3 * i + j] = fma(f[3 * i1 + j1], f[3 * i2 + j2], -f[3 * i1 + j2] * f[3 * i2 + j1]);
     }
+  // symmetric M: m00 m01 m02 m11 m12 m22
+  double m00 = fma(c[0], c[0], fma(c[3], c[3], c[6] * c[6]));
+  double m01 = fma(c[0], c[1], fma(c[3], c[4], c[6] * c[7]));
+  double m02 = fma(c[0], c[2], fma(c[3], c[5], c[6] * c[8]));
+  double m11 = fma(c[1], c[1], fma(c[4], c[4], c[7] * c[7]));
+  double m12 = fma(c[1], c[2], fma(c[4], c[5], c[7] * c[8]));
+  double m22 = fma(c[2], c[2], fma(c[5], c[5], c[8] * c[8]));
+  for (int it = 0; it < 40; ++it) {
+    const double tr = m00 + m11 + m22;
+    if (!(tr > 0.0)) break;                          // cof(F) = 0: F has rank <= 1, nothing to project
+    const double inv = 1.0 / tr;
+    m00 *= inv; m01 *= inv; m02 *= inv; m11 *= inv; m12 *= inv; m22 *= inv;
+    const double n00 = fma(m00, m00, fma(m01, m01, m02 * m02));
+    const double n01 = fma(m00, m01, fma(m01, m11, m02 * m12));
+    const double n02 = fma(m00, m02, fma(m01, m12, m02 * m22));
+    const double n11 = fma(m01, m01, fma(m11, m11, m12 * m12));
+    const double n12 = fma(m01, m02, fma(m11, m12, m12 * m22));
+    const double n22 = fma(m02, m02, fma(m12, m12, m22 * m22));
+    m00 = n00; m01 = n01; m02 = n02; m11 = n11; m12 = n12; m22 = n22;
+    if (1.0 - (n00 + n11 + n22) < 2e-8) break;
   }
-  // static selects (a dynamically indexed V[k][mi] would push S and V to local memory)
-  const bool use1 = S[1][1] < S[0][0];
-  const double m01 = use1 ? S[1][1] : S[0][0];
-  const bool use2 = S[2][2] < m01;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) out[k] = use2 ? V[k][2] : (use1 ? V[k][1] : V[k][0]);
+  // the column with the largest diagonal entry is the best-conditioned copy of v3
+  const bool use1 = m11 > m00;
+  const double d01 = use1 ? m11 : m00;
+  const bool use2 = m22 > d01;
+  const double a = use2 ? m02 : (use1 ? m01 : m00);
+  const double b = use2 ? m12 : (use1 ? m11 : m01);
+  const double g = use2 ? m22 : (use1 ? m12 : m02);
+  const double r = rsqrt(fma(a, a, fma(b, b, g * g)));
+  v[0] = a * r;
+  v[1] = b * r;
+  v[2] = g * r;
 }
 
+// AFFINE: the last row of Kinv is (0 0 1), so the dehomogenising divisions are by exactly 1.
+// KEYE: K = I, so the K^T F K product is the identity map.  Both are decided on the host.
+template <bool AFFINE, bool KEYE>
 __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count, int H,
     const int32_t* __restrict__ samples_in, uint64_t seed, int32_t* __restrict__ samples_out, const Mat3 K,
@@ -293,12 +290,18 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
     const double sx = c.x, sy = c.y, dx = c.z, dy = c.w;
     // x = Kinv [sx sy 1]^T, then dehomogenise (homography.py:228-237)
     const double* ki = Kinv.m;
-    const double w1 = fma(ki[6], sx, fma(ki[7], sy, ki[8]));
-    const double x = fma(ki[0], sx, fma(ki[1], sy, ki[2])) / w1;
-    const double y = fma(ki[3], sx, fma(ki[4], sy, ki[5])) / w1;
-    const double w2 = fma(ki[6], dx, fma(ki[7], dy, ki[8]));
-    const double u = fma(ki[0], dx, fma(ki[1], dy, ki[2])) / w2;
-    const double v = fma(ki[3], dx, fma(ki[4], dy, ki[5])) / w2;
+    double x = fma(ki[0], sx, fma(ki[1], sy, ki[2]));
+    double y = fma(ki[3], sx, fma(ki[4], sy, ki[5]));
+    double u = fma(ki[0], dx, fma(ki[1], dy, ki[2]));
+    double v = fma(ki[3], dx, fma(ki[4], dy, ki[5]));
+    if (!AFFINE) {
+      const double w1 = fma(ki[6], sx, fma(ki[7], sy, ki[8]));
+      const double w2 = fma(ki[6], dx, fma(ki[7], dy, ki[8]));
+      x /= w1;
+      y /= w1;
+      u /= w2;
+      v /= w2;
+    }
     A[k][0] = u * x; A[k][1] = u * y; A[k][2] = u;
     A[k][3] = v * x; A[k][4] = v * y; A[k][5] = v;
     A[k][6] = x;     A[k][7] = y;     A[k][8] = 1.0;
@@ -308,15 +311,17 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
 
   // rank-2 projection: F' = F - (F v3) v3^T, v3 = right-singular vector of the smallest
   // singular value (homography.py:244-246 zeroes S[2] only).
-  double S[3][3];
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) S[a][b] = fma(f[a], f[b], fma(f[3 + a], f[3 + b], f[6 + a] * f[6 + b]));
   double v3[3];
-  smallest_eigvec3(S, v3);
+  smallest_right_singular3(f, v3);
   double Fp[9];
   for (int r = 0; r < 3; ++r) {
     const double fv = fma(f[3 * r], v3[0], fma(f[3 * r + 1], v3[1], f[3 * r + 2] * v3[2]));
     for (int c = 0; c < 3; ++c) Fp[3 * r + c] = fma(-fv, v3[c], f[3 * r + c]);
+  }
+  if (KEYE) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) eo[k] = Fp[k];
+    return;
   }
   // E = K^T F' K  (homography.py:248)
   double T1[9];
@@ -347,8 +352,17 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
     Kinv.m[i] = Kinv_host ? Kinv_host[i] : ((i % 4 == 0) ? 1.0 : 0.0);
   }
   dim3 grid((H + kEpThreads - 1) / kEpThreads, n_pairs);
-  eight_point_kernel<<<grid, kEpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(corr), c_off, c_count, H, samples_in, seed, samples_out, K, Kinv, E_out);
+  const bool affine = Kinv.m[6] == 0.0 && Kinv.m[7] == 0.0 && Kinv.m[8] == 1.0;
+  bool keye = true;
+  for (int i = 0; i < 9; ++i) keye &= (K.m[i] == ((i % 4 == 0) ? 1.0 : 0.0));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* c4 = reinterpret_cast<const float4*>(corr);
+#define B2S_EP_LAUNCH(A_, K_) \
+  eight_point_kernel<A_, K_><<<grid, kEpThreads, 0, st>>>(c4, c_off, c_count, H, samples_in, seed, samples_out, K, Kinv, E_out)
+  if (affine && keye) B2S_EP_LAUNCH(true, true);
+  else if (affine) B2S_EP_LAUNCH(true, false);
+  else B2S_EP_LAUNCH(false, false);
+#undef B2S_EP_LAUNCH
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;
