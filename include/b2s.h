@@ -157,8 +157,10 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
 /* Diagnostics: when dev_buf != NULL (device memory, 8 x uint64 per SM) the i8 Hamming kernel
  * records, per CTA, clock64 totals: [0] MMA thread total, [1] MMA waiting for a free TMEM stage,
  * [2] MMA waiting for operand tiles, [3] producer waiting for a free ring slot, [4] epilogue
- * warp total, [5] epilogue waiting for accumulators, [6] tile pairs.  NULL switches it off. */
-void b2s_hamming_i8_debug(unsigned long long* dev_buf);
+ * warp total, [5] epilogue waiting for accumulators, [6] tile pairs.  NULL switches it off.
+ * mode (results become meaningless, timing only): bit 0 = the epilogue drains nothing,
+ * bit 1 = the operand ring is loaded once and then reused.  0 = normal operation. */
+void b2s_hamming_i8_debug(unsigned long long* dev_buf, int mode);
 
 /* Raw tcgen05.mma kind::i8 rate: every SM issues iters x 8 MMAs (M=128, N=n_dim in
  * {128,256}, K=32) from shared memory with no epilogue; *macs_out = int8 MACs issued. */

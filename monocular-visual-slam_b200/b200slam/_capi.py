@@ -67,7 +67,7 @@ def _declare(lib):
     lib.b2s_ransac_select.restype = i32
     lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
     lib.b2s_hamming_i8_debug.restype = None
-    lib.b2s_hamming_i8_debug.argtypes = [vp]
+    lib.b2s_hamming_i8_debug.argtypes = [vp, i32]
     lib.b2s_mma_microbench.restype = i32
     lib.b2s_mma_microbench.argtypes = [i32, i32, C.POINTER(dbl), vp]
     lib.b2s_tmem_microbench.restype = i32

@@ -25,22 +25,26 @@ for _ in range(3):
     m.knn2(batch)
 torch.cuda.synchronize()
 # MMA issue-rate microbenchmark, N = 128 and 256
-for nd in (128, 256):
+for nd, var in ((128, 0), (256, 0), (128, 1), (128, 2), (128, 3), (128, 4)):
     macs = C.c_double()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lib.b2s_mma_microbench(2000, nd, C.byref(macs), None)
+    arg = nd | (var << 16)
+    lib.b2s_mma_microbench(2000, arg, C.byref(macs), None)
     torch.cuda.synchronize()
-    e0.record(); lib.b2s_mma_microbench(2000, nd, C.byref(macs), None); e1.record(); torch.cuda.synchronize()
+    e0.record(); lib.b2s_mma_microbench(2000, arg, C.byref(macs), None); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"mma N={nd}: {2*macs.value/ms/1e12:.1f} TOP/s, {ms*1e-3*1.965e9/(2000*8):.1f} clk/instr")
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
-lib.b2s_hamming_i8_debug(C.c_void_p(dbg.data_ptr()))
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); m.knn2(batch); e1.record(); torch.cuda.synchronize()
-lib.b2s_hamming_i8_debug(None)
-d = dbg.cpu().numpy().reshape(148, 8).astype(np.float64)
-tp = d[:, 6]
-print(f"knn2 call {e0.elapsed_time(e1):.3f} ms; tile pairs/CTA mean {tp.mean():.0f}")
+    per = (18 if var else 8)
+    print(f"mma N={nd} variant {var}: {2*macs.value/ms/1e15:.2f} POP/s, {ms*1e-3*1.965e9/(2000*per):.1f} clk/instr")
 names = ["mma_total", "mma_wait_tempty", "mma_wait_full", "prod_wait_empty", "epi_total", "epi_wait_tfull"]
-for i, nm in enumerate(names):
-    print(f"{nm:18s} mean {d[:, i].mean():12.0f} clk  per tile pair {d[:, i].sum() / tp.sum():8.1f}")
+for mode in (0, 1, 2, 3):
+    dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    lib.b2s_hamming_i8_debug(C.c_void_p(dbg.data_ptr()), mode)
+    m.knn2(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); m.knn2(batch); e1.record(); torch.cuda.synchronize()
+    lib.b2s_hamming_i8_debug(None, 0)
+    d = dbg.cpu().numpy().reshape(148, 8).astype(np.float64)
+    tp = d[:, 6]
+    print(f"mode {mode} (bit0: no epilogue work, bit1: no ring reloads): knn2 call {e0.elapsed_time(e1):.3f} ms; tile pairs/CTA {tp.mean():.0f}")
+    print("   " + "  ".join(f"{nm} {d[:, i].sum() / tp.sum():.0f}" for i, nm in enumerate(names)))
