@@ -140,6 +140,84 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: S32 accumulate, signed 8-bit A and B, both K-major, M = 128, N = 128
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// The 18 MMAs of one tile pair as ONE asm block: 8 data K-steps + the index K-step into D1
+// (A = query tile, B = train tile), the same into D2 with the roles swapped.  After the 14th
+// MMA a non-consumed mbarrier.try_wait probes the barrier of the NEXT tile pair; its predicate
+// is only read after the last MMA has been queued, so the probe's latency (and the hardware
+// sleep until the phase completes) overlaps the MMA stream instead of idling the tensor pipe
+// at the tile boundary (~170 clk per blocking wait, b2s_mma_microbench variants 2 vs 3).
+// Returns 1 when the next tile pair's barrier phase was seen complete.
+__device__ __forceinline__ uint32_t tc_mma_tile_pair(uint32_t d1, uint32_t d2, uint64_t qdesc, uint64_t tdesc,
+                                                     uint64_t odesc, uint32_t idesc, uint64_t* next_bar,
+                                                     uint32_t next_parity, uint32_t has_next) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pnew, pprobe, pdone;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.eq.b32 pacc, 0, 0;\n\t"
+      "setp.ne.b32 pnew, 0, 0;\n\t"
+      "setp.ne.b32 pprobe, %9, 0;\n\t"
+      "setp.ne.b32 pdone, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %6, pnew;\n\t"
+      "add.u64 da, %3, 256;\n\t"
+      "add.u64 db, %4, 256;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 512;\n\t"
+      "add.u64 db, %4, 512;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 768;\n\t"
+      "add.u64 db, %4, 768;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 1024;\n\t"
+      "add.u64 db, %4, 1024;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 1280;\n\t"
+      "add.u64 db, %4, 1280;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 1536;\n\t"
+      "add.u64 db, %4, 1536;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 da, %3, 1792;\n\t"
+      "add.u64 db, %4, 1792;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %6, pacc;\n\t"
+      "add.u64 db, %4, 2048;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], %5, db, %6, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], %4, %3, %6, pnew;\n\t"
+      "add.u64 da, %4, 256;\n\t"
+      "add.u64 db, %3, 256;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 da, %4, 512;\n\t"
+      "add.u64 db, %3, 512;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 da, %4, 768;\n\t"
+      "add.u64 db, %3, 768;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 da, %4, 1024;\n\t"
+      "add.u64 db, %3, 1024;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "@pprobe mbarrier.try_wait.parity.shared::cta.b64 pdone, [%7], %8;\n\t"
+      "add.u64 da, %4, 1280;\n\t"
+      "add.u64 db, %3, 1280;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 da, %4, 1536;\n\t"
+      "add.u64 db, %3, 1536;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 da, %4, 1792;\n\t"
+      "add.u64 db, %3, 1792;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], da, db, %6, pacc;\n\t"
+      "add.u64 db, %3, 2048;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], %5, db, %6, pacc;\n\t"
+      "selp.u32 %0, 1, 0, pdone;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(d1), "r"(d2), "l"(qdesc), "l"(tdesc), "l"(odesc), "r"(idesc), "r"(smem_u32(next_bar)), "r"(next_parity),
+        "r"(has_next)
+      : "memory");
+  return ok;
+}
+
+
 #define TMEM_LD_X32(taddr, v)                                                                              \
   asm volatile(                                                                                            \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
@@ -311,6 +389,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t n = 0, g = 0;
+      bool probed = false;  // the barrier of the coming tile pair was already seen complete
       long long w_full = 0;
       const long long t_start = p.dbg ? clock64() : 0;
       const uint64_t odesc = make_smem_desc(smem_u32(s_ones));
@@ -324,23 +403,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
         const uint64_t qdesc = make_smem_desc(smem_u32(s_q + (size_t)qb * kI8TileBytes));
         for (int t = 0; t < n_tt; ++t, ++g) {
           const uint32_t s = g % kI8Stages, a = g & 1u;
-          const long long c0 = p.dbg ? clock64() : 0;
-          mbar_wait_bounded(&b_full[s], (g / kI8Stages) & 1u);  // operands landed AND TMEM stage a drained
-          if (p.dbg) w_full += clock64() - c0;
+          if (!probed) {  // operands landed AND TMEM stage a drained (first tile pair, item boundaries, late epilogue)
+            const long long c0 = p.dbg ? clock64() : 0;
+            mbar_wait_bounded(&b_full[s], (g / kI8Stages) & 1u);
+            if (p.dbg) w_full += clock64() - c0;
+          }
           tc_fence_after();
           const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
           const uint32_t d1 = tmem_base + a * 256u, d2 = d1 + 128u;
-          // K = 32 bytes per instruction = two k-chunks = 4096 B apart (descriptor units of 16 B: 256).
-          // Step 8 pairs the constant ones block with the B tile's index chunk (chunk 16).
-          constexpr uint64_t kIndex = 16u * (kI8ChunkBytes >> 4);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            tc_mma_i8(d1, qdesc + (uint64_t)k * 256u, tdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
-          tc_mma_i8(d1, odesc, tdesc + kIndex, kIdescI8, 1);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            tc_mma_i8(d2, tdesc + (uint64_t)k * 256u, qdesc + (uint64_t)k * 256u, kIdescI8, k > 0);
-          tc_mma_i8(d2, odesc, qdesc + kIndex, kIdescI8, 1);
+          const uint32_t gn = g + 1u;
+          probed = tc_mma_tile_pair(d1, d2, qdesc, tdesc, odesc, kIdescI8, &b_full[gn % kI8Stages],
+                                    (gn / kI8Stages) & 1u, (t + 1 < n_tt) ? 1u : 0u) != 0u;
           tc_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
           tc_commit(&b_tfull[a]);  // accumulators complete
         }
@@ -387,30 +460,29 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
           if (lane == 0) mbar_arrive(&b_full[(g + 2u) % kI8Stages]);
           continue;
         }
-        uint32_t v0[32], v1[32];
+        uint32_t v0[32], v1[32], v2[32], v3[32];
         uint32_t b[2] = {kNone, kNone}, s2[2] = {kNone, kNone}, m[2] = {kNone, kNone};
-        // D1 columns 0-63 | 64-127, D2 columns 0-63 | 64-127: each load is in flight while the
-        // previous 64 columns are folded
+        // D1 columns 0-63 | 64-127, D2 columns 0-63 | 64-127: 128 packed registers, all four
+        // loads in flight at once, and the TMEM stage goes back to the MMA thread as soon as
+        // they have landed — before any of the folding (the stage is held for the load latency
+        // only, so the MMA thread's probe of the next barrier finds it complete)
         TMEM_LD_X32P(lane_addr, v0);
-        tmem_ld_wait();
-        TMEM_REGS_READY(v0);
         TMEM_LD_X32P(lane_addr + 64u, v1);
-        fold_top2_p16(v0, b, s2);
-        tmem_ld_wait();
-        TMEM_REGS_READY(v1);
-        TMEM_LD_X32P(lane_addr + 128u, v0);
-        fold_top2_p16(v1, b, s2);
+        TMEM_LD_X32P(lane_addr + 128u, v2);
+        TMEM_LD_X32P(lane_addr + 192u, v3);
         tmem_ld_wait();
         TMEM_REGS_READY(v0);
-        TMEM_LD_X32P(lane_addr + 192u, v1);
-        fold_min_p16(v0, m);
-        tmem_ld_wait();
         TMEM_REGS_READY(v1);
+        TMEM_REGS_READY(v2);
+        TMEM_REGS_READY(v3);
         tc_fence_before();
         __syncwarp();
         // accumulator stage drained into registers: release it to tile pair g+2 (same stage)
         if (lane == 0) mbar_arrive(&b_full[(g + 2u) % kI8Stages]);
-        fold_min_p16(v1, m);
+        fold_top2_p16(v0, b, s2);
+        fold_top2_p16(v1, b, s2);
+        fold_min_p16(v2, m);
+        fold_min_p16(v3, m);
         // ---- per-row top-2 of this tile: merge the two chains, then the even / odd halves ----
         {
           const uint32_t bb = __vminu2(b[0], b[1]);
