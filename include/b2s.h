@@ -43,7 +43,8 @@ extern "C" {
 
 /* Hamming kernel variants */
 #define B2S_VARIANT_POPC 0  /* LOP3/POPC integer-pipe kernel (K1) */
-#define B2S_VARIANT_I8MMA 1 /* tcgen05.mma kind::i8 +-1 contraction (K2) */
+#define B2S_VARIANT_I8MMA 1 /* tcgen05.mma kind::i8 +-8 contraction, two products D and D^T (K2) */
+#define B2S_VARIANT_I8MMA1 2 /* same contraction, ONE product; column minima by warp butterfly (K2s) */
 
 int b2s_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py gpu_launches). */

@@ -172,7 +172,7 @@ class HammingMatcher:
         fs = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
         bb = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
         ws_ptr, ws_bytes = None, 0
-        if nq > 0 and (self.variant == _capi.VARIANT_I8MMA or self.t_split != 1):
+        if nq > 0 and (self.variant != _capi.VARIANT_POPC or self.t_split != 1):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             want = self.t_split if self.t_split > 1 else max(1, min(64, (4 * sms) // max(1, b.n_pairs)))
             ws_bytes = int(self._lib.b2s_hamming_workspace_bytes_v(self.variant, b.n_pairs, nq, b.max_nq, b.max_nt, want))

@@ -44,7 +44,7 @@ size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt);
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
-                      size_t workspace_bytes, cudaStream_t st);
+                      size_t workspace_bytes, int single, cudaStream_t st);
 
 void hamming_i8_set_debug(unsigned long long* dev_buf, int mode);
 int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st);
@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
         if (WHICH == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(c1), "r"(c2));
         if (WHICH == 7) asm volatile("redux.sync.min.s32 %0, %0, 0xffffffff;" : "+r"(x[k]));
         if (WHICH == 8) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x[k]));
+        if (WHICH == 9) x[k] = __vminu2(x[k], c2 + it);                      // VIMNMX.U16x2
+        if (WHICH == 10) x[k] = __vimin3_u16x2(x[k], c1 + it, c2);           // VIMNMX3.U16x2
+        if (WHICH == 11) x[k] = __viaddmax_u16x2(x[k], c1, c2);              // VIADDMNMX.U16x2
+        if (WHICH == 12)  // SEL with a loop-invariant predicate
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, 5;\n\tselp.b32 %0, %0, %1, p;\n\t}" : "+r"(x[k]) : "r"(c1), "r"(c2));
+        if (WHICH == 13) asm volatile("prmt.b32 %0, %0, %1, 0x1032;" : "+r"(x[k]) : "r"(c1));
       }
     }
   }
@@ -138,16 +144,18 @@ int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const
                                max_nq, max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
                                st);
   }
-  if (variant == B2S_VARIANT_I8MMA) {
+  if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1) {
     return hamming_i8_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt, max_nq,
-                             max_nt, fwd_best, fwd_second, bwd_best, workspace, workspace_bytes, st);
+                             max_nt, fwd_best, fwd_second, bwd_best, workspace, workspace_bytes,
+                             variant == B2S_VARIANT_I8MMA1, st);
   }
   set_error("Hamming variant %d is not built into this library", variant);
   return B2S_ERR_UNSUPPORTED;
 }
 
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
-  if (variant == B2S_VARIANT_I8MMA) return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
+  if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1)
+    return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
   return b2s_hamming_workspace_bytes(total_nq, t_split);
 }
 
@@ -163,7 +171,7 @@ int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink,
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(which >= 0 && which <= 8, "which must be 0..8");
+  B2S_REQUIRE(which >= 0 && which <= 13, "which must be 0..13");
   B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
   const int grid = sm_count() * ctas_per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -176,6 +184,11 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     case 5: pipe_kernel<5><<<grid, 256, 0, st>>>(iters, sink); break;
     case 7: pipe_kernel<7><<<grid, 256, 0, st>>>(iters, sink); break;
     case 8: pipe_kernel<8><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 9: pipe_kernel<9><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 10: pipe_kernel<10><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 11: pipe_kernel<11><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 12: pipe_kernel<12><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 13: pipe_kernel<13><<<grid, 256, 0, st>>>(iters, sink); break;
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }
   B2S_CUDA(cudaGetLastError());

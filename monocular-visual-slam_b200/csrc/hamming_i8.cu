@@ -59,16 +59,28 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
   return train ? (0xF8F8F8F8u - sp * 0xF0u) : (0x08080808u + sp * 0xF0u);
 }
 
+// layout 0: two-product tiles (17 chunks; index chunk [r, 64 x4, 0..], padding rows [127 x9, 0..]).
+// layout 1 / 2: single-product query / train tiles.  There the index K-step multiplies the
+// QUERY tile's own chunk 16 (A side) with the TRAIN tile's chunk 16 (B side), 14 int8 slots:
+//     A valid  [1, 64 x4, r, 0 x4, 64 x4]      B valid  [c, 64 x4, 1, 64 x4, 0 x4]
+//     A pad    [1, 127 x4, 127, 127 x4, 0 x4]  B pad    [127, 127 x4, 1, 0 x4, 127 x4]
+// valid.valid = c + r + 2^14 (cancels the data bias), valid.pad = 65151 + r, pad.valid =
+// 65151 + c: the accumulator is 128*ham + column + row for real pairs and lands in the padding
+// range (>= 0xFE00 after the row or the column is taken off again) otherwise.  Query tiles
+// carry an 18th, all-zero chunk so that the second half of the K = 32 index step multiplies
+// whatever follows the train tile's chunk 16 in shared memory by zero.
 __global__ void __launch_bounds__(256) expand_pm8_kernel(const uint8_t* __restrict__ desc,
                                                          const int32_t* __restrict__ off,
                                                          const int32_t* __restrict__ src, int tiles_per_pair,
-                                                         int train, uint4* __restrict__ out) {
+                                                         int train, int layout, uint4* __restrict__ out) {
+  const int chunks = (layout == 1) ? kI8Chunks + 1 : kI8Chunks;
+  const int units = chunks * kI8Tile;
   const int pair = blockIdx.y;
   const int o = off[pair];
   const int n = off[pair + 1] - o;
   const int in0 = src ? src[pair] : o;
   const int u = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte unit within the pair's tiles
-  const int tile = u / kI8Units, w = u - tile * kI8Units;
+  const int tile = u / units, w = u - tile * units;
   if (tile >= tiles_per_pair) return;
   if (tile * kI8Tile >= n) return;  // tile never read
   const int kc = w >> 7, r = w & 127;
@@ -83,15 +95,25 @@ __global__ void __launch_bounds__(256) expand_pm8_kernel(const uint8_t* __restri
       v.z = spread4((bits >> 8) & 15u, train);
       v.w = spread4((bits >> 12) & 15u, train);
     }
-  } else if (row < n) {
-    v.x = (uint32_t)r | 0x40404000u;                     // index chunk: [r, 64, 64, 64, 64, 0, ...]
-    v.y = 0x00000040u;
-  } else {
-    v.x = 0x7F7F7F7Fu;                                   // padding row: [127 x9, 0, ...] -> acc = 65151
-    v.y = 0x7F7F7F7Fu;
-    v.z = 0x0000007Fu;
-  }
-  out[((size_t)pair * tiles_per_pair + tile) * kI8Units + w] = v;
+  } else if (kc == 16) {
+    if (layout == 0) {
+      if (row < n) {
+        v.x = (uint32_t)r | 0x40404000u;                 // [r, 64, 64, 64, 64, 0, ...]
+        v.y = 0x00000040u;
+      } else {
+        v.x = 0x7F7F7F7Fu;                               // [127 x9, 0, ...] -> acc = 65151
+        v.y = 0x7F7F7F7Fu;
+        v.z = 0x0000007Fu;
+      }
+    } else if (layout == 1) {
+      if (row < n) v = make_uint4(0x40404001u, 0x00000040u | ((uint32_t)r << 8), 0x40400000u, 0x00004040u);
+      else v = make_uint4(0x7F7F7F01u, 0x7F7F7F7Fu, 0x00007F7Fu, 0u);
+    } else {
+      if (row < n) v = make_uint4(0x40404000u | (uint32_t)r, 0x40400140u, 0x00004040u, 0u);
+      else v = make_uint4(0x7F7F7F7Fu, 0x0000017Fu, 0x7F7F0000u, 0x00007F7Fu);
+    }
+  }  // kc == 17 (layout 1): zeros
+  out[((size_t)pair * tiles_per_pair + tile) * units + w] = v;
 }
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------
@@ -115,6 +137,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one elected lane of a converged warp (ptxas then knows the tcgen05 instructions below it are
+// issued by a single thread and drops the per-instruction election loop it emits otherwise)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t is_leader;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+  return is_leader != 0u;
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t n = 0, g = 0;
       bool probed = false;  // the barrier of the coming tile pair was already seen complete
       long long w_full = 0;
@@ -526,6 +555,369 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
   }
 }
 
+// =====================================================================================
+// Single-product variant (B2S_VARIANT_I8MMA1): D = Qtile . Ttile^T only.
+//
+// The two-product kernel above spends half of its tensor time on D^T just to make the column
+// minimum a per-thread reduction.  Here the column minimum comes out of D itself: after the
+// index K-step adds the ROW as well as the column (acc = ham*128 + column + row), so the very
+// registers the per-row top-2 was folded from also order a column's entries by (ham, row), and
+// a 5-step butterfly over the 32 lanes of a warp (SUB, IMAD, IMAD, SHFL.BFLY, VIMNMX.U16x2 per
+// surviving register; 62 shuffles) leaves lane L with the minima of columns 4L..4L+3 over the
+// warp's 32 rows.  Each lane widens its four keys and sends them to bwd_best with atomicMin — but only
+// those that beat the current value, which it prefetched before waiting for the accumulator
+// (a stale value merely costs a redundant atomic; ~ln(64) of the 64 candidates per train row
+// and pair survive the filter).
+// Work item = (pair, 256-query block): both 128-row sub-tiles stay in shared memory while
+// the train tiles stream past once, which halves the L2 -> SM operand traffic (at ~650 clk per
+// tile pair 34 KB per tile pair would exceed the L2 slice throughput of the chip).
+// Four TMEM stages of 128 columns (tile pair g uses stage g%4); epilogue set e owns sub-tile e
+// (stages e and e+2), so a thread keeps its row's running top-2 in registers for the whole
+// item and nothing is merged at the end, and the MMA thread runs up to four tile pairs ahead.
+// One barrier per tile pair ("go"): operands landed + TMEM stage drained, probed from inside
+// the MMA stream as above.
+constexpr int kI8sGo = 16;  // go barriers: the producer runs up to 8 tile pairs ahead of the MMA thread
+constexpr int kI8sQTileBytes = (kI8Chunks + 1) * kI8ChunkBytes;  // query tiles carry a zero chunk 17
+
+__device__ __forceinline__ uint32_t tc_mma_tile_single(uint32_t d, uint64_t qdesc, uint64_t tdesc, uint32_t idesc,
+                                                       uint64_t* next_bar, uint32_t next_parity, uint32_t has_next) {
+  // 8 data K-steps + the index K-step (chunks 16/17 of the query tile x chunk 16 of the train tile)
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pnew, pprobe, pdone;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.eq.b32 pacc, 0, 0;\n\t"
+      "setp.ne.b32 pnew, 0, 0;\n\t"
+      "setp.ne.b32 pprobe, %7, 0;\n\t"
+      "setp.ne.b32 pdone, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], %2, %3, %4, pnew;\n\t"
+      "add.u64 da, %2, 256;\n\t"
+      "add.u64 db, %3, 256;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 512;\n\t"
+      "add.u64 db, %3, 512;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 768;\n\t"
+      "add.u64 db, %3, 768;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 1024;\n\t"
+      "add.u64 db, %3, 1024;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "@pprobe mbarrier.try_wait.parity.shared::cta.b64 pdone, [%5], %6;\n\t"
+      "add.u64 da, %2, 1280;\n\t"
+      "add.u64 db, %3, 1280;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 1536;\n\t"
+      "add.u64 db, %3, 1536;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 1792;\n\t"
+      "add.u64 db, %3, 1792;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "add.u64 da, %2, 2048;\n\t"
+      "add.u64 db, %3, 2048;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], da, db, %4, pacc;\n\t"
+      "selp.u32 %0, 1, 0, pdone;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(d), "l"(qdesc), "l"(tdesc), "r"(idesc), "r"(smem_u32(next_bar)), "r"(next_parity), "r"(has_next)
+      : "memory");
+  return ok;
+}
+
+// One butterfly step over N live registers: lanes with up = 1 keep the upper half and send the
+// lower one.  The choice is arithmetic, not SEL: every ALU-pipe instruction (SEL, LOP3, PRMT,
+// VIMNMX) issues at 64 threads/clk/SM on this part (tools/pipe_rates.py) and so does IMAD on
+// the FMA pipe; the epilogue is bound by whichever of the two pipes carries more, so the
+// selection goes to the FMA pipe (3 instructions) and only the minimum stays on the ALU pipe.
+//   e = a - b;  send = up*e + b  (= up ? a : b);  keep = (-up)*e + a  (= up ? b : a)   (exact mod 2^32)
+template <int N>
+__device__ __forceinline__ void colmin_step(uint32_t (&y)[64], uint32_t up, uint32_t nup, int lane_mask) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    uint32_t send, keep;
+    if (i % 5 == 4) {
+      // every fifth exchange selects on the ALU pipe instead (2 SEL): with ~205 other ALU-pipe and
+      // ~77 other FMA-pipe instructions per tile pair this split levels the two pipes
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tselp.b32 %0, %2, %3, p;\n\tselp.b32 %1, %3, %2, p;\n\t}"
+          : "=r"(send), "=r"(keep)
+          : "r"(y[i]), "r"(y[i + N / 2]), "r"(up));
+    } else {
+      asm("{\n\t.reg .u32 e;\n\tsub.u32 e, %2, %3;\n\tmad.lo.u32 %0, %4, e, %3;\n\tmad.lo.u32 %1, %5, e, %2;\n\t}"
+          : "=r"(send), "=r"(keep)
+          : "r"(y[i]), "r"(y[i + N / 2]), "r"(up), "r"(nup));
+    }
+    y[i] = __vminu2(keep, __shfl_xor_sync(0xFFFFFFFFu, send, lane_mask));
+  }
+}
+
+// Column minima of a 32-row x 128-column slab held one row per lane (64 packed registers).
+// The accumulator already is ham*128 + column + row (see expand_pm8_kernel): within a column
+// (= a register half) the column is the same constant for all lanes, so the unsigned order is
+// the (ham, row) order; rows past the end of the pair arrive as padding keys from the MMA.
+// Five butterfly steps leave lane L with columns 4L..4L+3 in y[0] | y[1]; the column constant
+// is taken off those two registers at the end.
+__device__ __forceinline__ void colmin_warp(uint32_t (&y)[64], int lane) {
+  uint32_t u16 = (lane >> 4) & 1, u8 = (lane >> 3) & 1, u4 = (lane >> 2) & 1, u2 = (lane >> 1) & 1, u1 = lane & 1;
+  colmin_step<64>(y, u16, 0u - u16, 16);
+  colmin_step<32>(y, u8, 0u - u8, 8);
+  colmin_step<16>(y, u4, 0u - u4, 4);
+  colmin_step<8>(y, u2, 0u - u2, 2);
+  colmin_step<4>(y, u1, 0u - u1, 1);
+  const uint32_t cfix = (uint32_t)(4 * lane) * 0x10001u + 0x00010000u;  // columns 4L | 4L+1 of y[0]
+  y[0] -= cfix;
+  y[1] -= cfix + 0x00020002u;                                            // columns 4L+2 | 4L+3
+}
+
+__global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_q = smem;                                   // 2 x 36 KB: sub-tile a | sub-tile b of the item (18 chunks each)
+  uint8_t* s_t = smem + 2 * kI8sQTileBytes;              // kI8Stages x 34 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_t + kI8Stages * kI8TileBytes + kI8ChunkBytes);  // +1 chunk: see below
+  uint64_t* b_go = bars;                                 // [kI8sGo]
+  uint64_t* b_empty = bars + kI8sGo;                     // [kI8Stages]
+  uint64_t* b_tfull = bars + kI8sGo + kI8Stages;         // [4] one per TMEM stage
+  uint64_t* b_qempty = bars + kI8sGo + kI8Stages + 4;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kI8sGo + kI8Stages + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_blocks = (p.q_tiles + 1) >> 1;
+  const int n_items = p.n_pairs * q_blocks;
+
+  // the index K-step reads one chunk past the last ring slot (times the query tile's zero chunk):
+  // keep that chunk inside the allocation and defined
+  for (int i = threadIdx.x; i < kI8Tile; i += kI8Threads)
+    reinterpret_cast<uint4*>(s_t + kI8Stages * kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kI8sGo; ++k) mbar_init(&b_go[k], 5);  // producer + the 4 warps that drained tile pair g-4
+    for (int s = 0; s < kI8Stages; ++s) mbar_init(&b_empty[s], 1);
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(&b_tfull[a], 1);
+      for (int k = 0; k < 4; ++k) mbar_arrive(&b_go[a]);  // tile pairs 0..3 find their TMEM stage free
+    }
+    for (int a = 0; a < 2; ++a) mbar_init(&b_qempty[a], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  // all roles walk the same items; an item always has 2 * n_tt tile pairs (sub-tile b may be
+  // all padding: its MMAs then read stale shared memory and every result is ignored)
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t n = 0, tau = 0;  // items / train tiles seen by this CTA
+      long long w_empty = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int pair = w / q_blocks, qb = w - pair * q_blocks;
+        const int nq = p.q_off[pair + 1] - p.q_off[pair];
+        const int nt = p.t_off[pair + 1] - p.t_off[pair];
+        const int q0 = qb * 2 * kI8Tile;
+        if (q0 >= nq || nt == 0) continue;
+        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+        const bool has_b = q0 + kI8Tile < nq;
+        const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
+        const uint8_t* qsrc = p.qx + ((size_t)pair * p.q_tiles + 2 * qb) * kI8sQTileBytes;
+        for (int t = 0; t < n_tt; ++t, ++tau) {
+          const uint32_t s = tau % kI8Stages, g = 2u * tau;
+          uint64_t* go_a = &b_go[g % kI8sGo];
+          uint64_t* go_b = &b_go[(g + 1u) % kI8sGo];
+          const long long c0 = p.dbg ? clock64() : 0;
+          if (tau >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((tau / kI8Stages) - 1u) & 1u);
+          if (p.dbg) w_empty += clock64() - c0;
+          const bool skip_t = (p.mode & 2) && tau >= kI8Stages;
+          if (t == 0) {
+            if (n >= 1) mbar_wait_bounded(&b_qempty[0], (n - 1u) & 1u);
+            mbar_arrive_expect_tx(go_a, kI8sQTileBytes + (skip_t ? 0 : kI8TileBytes));
+            bulk_g2s(s_q, qsrc, kI8sQTileBytes, go_a);
+          } else if (skip_t) {
+            mbar_arrive(go_a);
+          } else {
+            mbar_arrive_expect_tx(go_a, kI8TileBytes);
+          }
+          if (!skip_t) bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, go_a);
+          if (t == 0 && has_b) {
+            if (n >= 1) mbar_wait_bounded(&b_qempty[1], (n - 1u) & 1u);
+            mbar_arrive_expect_tx(go_b, kI8sQTileBytes);
+            bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kI8sQTileBytes, go_b);
+          } else {
+            mbar_arrive(go_b);
+          }
+        }
+        ++n;
+      }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      uint32_t g = 0;
+      bool probed = false;
+      long long w_full = 0;
+      const long long t_start = p.dbg ? clock64() : 0;
+      const uint64_t qdesc_a = make_smem_desc(smem_u32(s_q));
+      const uint64_t qdesc_b = make_smem_desc(smem_u32(s_q + kI8sQTileBytes));
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int pair = w / q_blocks, qb = w - pair * q_blocks;
+        const int nq = p.q_off[pair + 1] - p.q_off[pair];
+        const int nt = p.t_off[pair + 1] - p.t_off[pair];
+        if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
+        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+        for (int t = 0; t < n_tt; ++t) {
+          const uint32_t s = (g >> 1) % kI8Stages;
+          const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
+#pragma unroll
+          for (uint32_t sub = 0; sub < 2; ++sub, ++g) {
+            if (!probed) {  // first tile pair, item boundaries, late epilogue or late loads
+              const long long c0 = p.dbg ? clock64() : 0;
+              mbar_wait_bounded(&b_go[g % kI8sGo], (g / kI8sGo) & 1u);
+              if (p.dbg) w_full += clock64() - c0;
+            }
+            tc_fence_after();
+            const uint32_t gn = g + 1u;
+            const uint32_t more = (sub == 0 || t + 1 < n_tt) ? 1u : 0u;
+            probed = tc_mma_tile_single(tmem_base + (g & 3u) * 128u, sub ? qdesc_b : qdesc_a, tdesc, kIdescI8,
+                                        &b_go[gn % kI8sGo], (gn / kI8sGo) & 1u, more) != 0u;
+            if (sub == 1) tc_commit(&b_empty[s]);          // train tile consumed by both sub-tiles
+            tc_commit(&b_tfull[g & 3u]);                    // accumulator stage complete
+            if (t == n_tt - 1) tc_commit(&b_qempty[sub]);   // the item's last use of this query sub-tile
+          }
+        }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_start);
+        p.dbg[blockIdx.x * 8 + 1] = 0ull;
+        p.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full;
+        p.dbg[blockIdx.x * 8 + 6] = g;
+      }
+    }
+  } else {
+    // ===== epilogue: set = sub-tile, owning TMEM stages sub and sub+2 alternately; warp%4 = TMEM lane quarter =====
+    const int quarter = warp & 3;
+    const uint32_t sub = (uint32_t)(warp - 2) >> 2;
+    const int row = quarter * 32 + lane;  // TMEM lane = row of the sub-tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t h = 0;  // tile pairs handled by this set
+    long long w_tfull = 0;
+    const long long e_start = p.dbg ? clock64() : 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int pair = w / q_blocks, qb = w - pair * q_blocks;
+      const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
+      const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
+      const int q0 = qb * 2 * kI8Tile + (int)sub * kI8Tile;   // first query row of this set's sub-tile
+      if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
+      const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+      const int rows_valid = max(0, min(kI8Tile, nq - q0));
+      uint32_t gbest = kNone, gsecond = kNone;
+      for (int t = 0; t < n_tt; ++t, ++h) {
+        const uint32_t g = 2u * h + sub;
+        const int tbase = t * kI8Tile;
+        const int nt_valid = min(kI8Tile, nt - tbase);
+        const uint32_t stage = g & 3u;
+        const uint32_t lane_addr = lane_base + stage * 128u;
+        // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics)
+        uint32_t cur[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * lane + k;
+          cur[k] = (c < nt_valid) ? __ldcg(&p.bwd_best[to + tbase + c]) : 0u;
+        }
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait_bounded(&b_tfull[stage], (h >> 1) & 1u);
+        if (p.dbg) w_tfull += clock64() - c0;
+        tc_fence_after();
+        if (p.mode & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_go[(g + 4u) % kI8sGo]);
+          continue;
+        }
+        uint32_t v0[32], v1[32];
+        TMEM_LD_X32P(lane_addr, v0);
+        TMEM_LD_X32P(lane_addr + 64u, v1);
+        tmem_ld_wait();
+        TMEM_REGS_READY(v0);
+        TMEM_REGS_READY(v1);
+        tc_fence_before();
+        __syncwarp();
+        // accumulator drained into registers: the stage goes to tile pair g+4 (same sub-tile, two train tiles on)
+        if (lane == 0) mbar_arrive(&b_go[(g + 4u) % kI8sGo]);
+        // ---- per-row top-2 of this tile, two passes over the 64 packed registers ----
+        // pass 1: minimum per 16-bit lane (even / odd columns), VIMNMX3: 0.5 instruction per register.
+        // pass 2: keys are unique within a row (the column is part of the key), so with c = ~best
+        // (= -(best + 1) per half-word) the wrapped sum x + c is 0xFFFF exactly for the minimum itself
+        // and x - best - 1 (order preserving) for everything else; VIADDMNMX.U16x2 adds and takes
+        // the running minimum in ONE instruction per register.  1.5 per register instead of 2.5.
+        {
+          uint32_t m[2] = {kNone, kNone}, a2[2] = {kNone, kNone};
+          fold_min_p16(v0, m);
+          fold_min_p16(v1, m);
+          const uint32_t bb = __vminu2(m[0], m[1]);
+          const uint32_t cneg = ~bb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            a2[0] = __viaddmin_u16x2(v0[j], cneg, a2[0]);
+            a2[1] = __viaddmin_u16x2(v0[j + 1], cneg, a2[1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            a2[0] = __viaddmin_u16x2(v1[j], cneg, a2[0]);
+            a2[1] = __viaddmin_u16x2(v1[j + 1], cneg, a2[1]);
+          }
+          const uint32_t ss = __vminu2(a2[0], a2[1]) + bb + 0x00010001u;  // second per 16-bit lane (no carry: < 2^16 each)
+          const uint32_t bw = swap16(bb);
+          const uint32_t best16 = __vminu2(bb, bw);
+          const uint32_t sec16 = __vimin3_u16x2(__vmaxu2(bb, bw), ss, swap16(ss));
+          // keys carry + row (constant per thread): take it off before widening
+          top2_insert(gbest, gsecond, key16_to_key32((best16 & 0xFFFFu) - (uint32_t)row, (uint32_t)tbase));
+          top2_insert(gbest, gsecond, key16_to_key32((sec16 & 0xFFFFu) - (uint32_t)row, (uint32_t)tbase));
+        }
+        // ---- column minima: butterfly over the warp on the very same registers ----
+        uint32_t y[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          y[j] = v0[j];
+          y[j + 32] = v1[j];
+        }
+        colmin_warp(y, lane);
+        // lane L now holds columns 4L..4L+3 (y[0] = 4L | 4L+1, y[1] = 4L+2 | 4L+3) over this warp's 32 rows;
+        // a candidate that does not beat the (possibly stale) current minimum needs no atomic
+        const uint32_t cm16[4] = {y[0] & 0xFFFFu, y[0] >> 16, y[1] & 0xFFFFu, y[1] >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t key = key16_to_key32(cm16[k], (uint32_t)q0);
+          // rows_valid == 0: the whole sub-tile is padding and its MMAs read stale shared memory
+          if (rows_valid > 0 && cm16[k] < kKey16Valid && key < cur[k]) atomicMin(&p.bwd_best[to + tbase + 4 * lane + k], key);
+        }
+      }
+      if (row < rows_valid) {
+        p.fwd_best[qo + q0 + row] = gbest >= kKey32Pad ? kNone : gbest;
+        p.fwd_second[qo + q0 + row] = gsecond >= kKey32Pad ? kNone : gsecond;
+      }
+    }
+    if (p.dbg && threadIdx.x == 64) {
+      p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
+      p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+
 // ---- measurement: raw tcgen05.mma kind::i8 issue rate (no epilogue), one CTA per SM ------
 // n_dim = 128 or 256; A = 128 rows, B = n_dim rows, both in the canonical no-swizzle layout.
 // variant 0: 8 accumulating MMAs per iteration, nothing else.
@@ -663,15 +1055,18 @@ void hamming_i8_set_debug(unsigned long long* dev_buf, int mode) {
 constexpr size_t kI8SmemBytes =
     (size_t)(2 + kI8Stages) * kI8TileBytes + 2 * kI8ChunkBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
+constexpr size_t kI8sSmemBytes = 2 * (size_t)kI8sQTileBytes + (size_t)kI8Stages * kI8TileBytes + kI8ChunkBytes +
+                                 8 * (kI8sGo + kI8Stages + 6) + 16;
+
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
-  return (size_t)n_pairs * (qt + tt) * kI8TileBytes;
+  return (size_t)n_pairs * (qt * kI8sQTileBytes + tt * kI8TileBytes);  // sized for the larger (single-product) layout
 }
 
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
-                      size_t workspace_bytes, cudaStream_t st) {
+                      size_t workspace_bytes, int single, cudaStream_t st) {
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
   if (total_nq > 0) {  // rows of pairs without train descriptors keep "none"
@@ -684,12 +1079,13 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "i8 variant needs %zu workspace bytes (b2s_hamming_workspace_bytes_v), got %zu", need, workspace_bytes);
   B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
+  const int q_units = (single ? kI8Chunks + 1 : kI8Chunks) * kI8Tile;
   uint8_t* qx = static_cast<uint8_t*>(workspace);
-  uint8_t* tx = qx + (size_t)n_pairs * qt * kI8TileBytes;
-  expand_pm8_kernel<<<dim3((qt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt, 0,
-                                                                                reinterpret_cast<uint4*>(qx));
+  uint8_t* tx = qx + (size_t)n_pairs * qt * q_units * 16;
+  expand_pm8_kernel<<<dim3((qt * q_units + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt, 0, single ? 1 : 0,
+                                                                               reinterpret_cast<uint4*>(qx));
   B2S_CUDA(cudaGetLastError());
-  expand_pm8_kernel<<<dim3((tt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt, 1,
+  expand_pm8_kernel<<<dim3((tt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt, 1, single ? 2 : 0,
                                                                                 reinterpret_cast<uint4*>(tx));
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
@@ -712,6 +1108,20 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.n_pairs = n_pairs;
   p.dbg = g_i8_dbg;
   p.mode = g_i8_mode;
+  if (single) {
+    static bool attr_set1 = false;
+    if (!attr_set1) {
+      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kI8sSmemBytes));
+      attr_set1 = true;
+    }
+    const long items = (long)((qt + 1) / 2) * n_pairs;
+    const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
+    hamming_knn2_i8s_kernel<<<grid, kI8Threads, kI8sSmemBytes, st>>>(p);
+    B2S_CUDA(cudaGetLastError());
+    note_launch();
+    return B2S_OK;
+  }
   const long items = (long)qt * n_pairs;
   const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
   hamming_knn2_i8_kernel<<<grid, kI8Threads, kI8SmemBytes, st>>>(p);

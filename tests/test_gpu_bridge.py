@@ -125,7 +125,7 @@ def test_sequence_tracker_equals_independent_pairs():
     desc, kp = tracking_sequence(F, N, seed=7)
     counts = np.array([700, 650, 700, 512, 700, 699], np.int32)
     cfg = FrontendConfig(hypotheses=128, max_matches=300)
-    for variant in (_capi.VARIANT_POPC, _capi.VARIANT_I8MMA):
+    for variant in (_capi.VARIANT_POPC, _capi.VARIANT_I8MMA, _capi.VARIANT_I8MMA1):
         tr = SequenceTracker(F, N, cfg, variant=variant, chunks=3)
         out = tr.run(torch.from_numpy(desc.reshape(-1, 32)).pin_memory(), torch.from_numpy(kp.reshape(-1, 2)).pin_memory(), counts)
         torch.cuda.synchronize()

@@ -198,11 +198,11 @@ def test_bad_arguments_raise(matcher):
 
 # ---- K2: tcgen05 kind::i8 variant, same contract, same bit-exact bar -------------------
 
-@pytest.fixture(scope="module")
-def matcher_i8():
+@pytest.fixture(scope="module", params=["two_products", "single_product"])
+def matcher_i8(request):
     from b200slam import _capi
     from b200slam.frontend import HammingMatcher
-    return HammingMatcher(variant=_capi.VARIANT_I8MMA)
+    return HammingMatcher(variant=_capi.VARIANT_I8MMA if request.param == "two_products" else _capi.VARIANT_I8MMA1)
 
 
 def test_i8_variant_golden_bit_exact(hg, matcher_i8):
@@ -217,7 +217,7 @@ def test_i8_variant_golden_bit_exact(hg, matcher_i8):
 
 def test_i8_variant_ragged_and_large(matcher_i8, matcher):
     rng = np.random.default_rng(21)
-    sizes = [(int(rng.integers(1, 900)), int(rng.integers(1, 900))) for _ in range(10)] + [(0, 7), (7, 0), (128, 128), (129, 127), (2000, 2000), (1944, 2000)]
+    sizes = [(int(rng.integers(1, 900)), int(rng.integers(1, 900))) for _ in range(10)] + [(0, 7), (7, 0), (128, 128), (129, 127), (256, 300), (257, 1), (1, 257), (384, 385), (2000, 2000), (1944, 2000)]
     for alphabet in (256, 4):
         qs = [rng.integers(0, alphabet, (a, 32), dtype=np.uint8) for a, _ in sizes]
         ts = [rng.integers(0, alphabet, (b, 32), dtype=np.uint8) for _, b in sizes]
