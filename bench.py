@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--hyps", type=int, default=2000)
     ap.add_argument("--cpu-pairs", type=int, default=0, help="CPU baseline sample size (0 = one per core, min 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", default="i8", choices=["popc", "i8"], help="Hamming kernel: K1 POPC or K2 tcgen05 kind::i8")
+    ap.add_argument("--variant", default="i8s", choices=["popc", "i8", "i8s"],
+                    help="Hamming kernel: K1 POPC, K2 tcgen05 kind::i8 with two products, K2s single product (shipped default)")
     ap.add_argument("--chunks", type=int, default=4, help="e2e: copy/compute overlap chunks")
     ap.add_argument("--sweep", action="store_true", help="also time every POPC-kernel configuration (extra key)")
     return ap.parse_args()
@@ -151,7 +152,7 @@ def b200_main(a):
     import torch.distributed as dist
 
     from b200slam import _capi
-    from b200slam.frontend import Frontend, FrontendConfig, PairBatch, pipe_microbench
+    from b200slam.frontend import Frontend, FrontendConfig, PairBatch, mma_microbench, pipe_microbench
     from b200slam.synthetic import tracking_sequence
 
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +171,8 @@ def b200_main(a):
     desc_np, kp_np = tracking_sequence(a.pairs + 1, a.nfeat, seed=1234 + rank)
     counts = np.full(a.pairs + 1, a.nfeat, np.int32)
     cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337 + rank)
-    variant = _capi.VARIANT_I8MMA if a.variant == "i8" else _capi.VARIANT_POPC
+    VARIANTS = {"popc": _capi.VARIANT_POPC, "i8": _capi.VARIANT_I8MMA, "i8s": _capi.VARIANT_I8MMA1}
+    variant = VARIANTS[a.variant]
     fe = Frontend(cfg, variant=variant)
     desc_host = torch.from_numpy(desc_np.reshape(-1, 32)).pin_memory()
     kp_host = torch.from_numpy(kp_np.reshape(-1, 2)).pin_memory()
@@ -231,11 +233,14 @@ def b200_main(a):
         fe.matcher.knn2(batch)
     k1_ms = timed(k1, a.steps, a.warmup)
     k1_avg = float(np.mean(k1_ms)) * 1e-3
-    # the other variant, for the K1-vs-K2 decision record
+    # the other variants, for the K1 / K2 / K2s decision record
     from b200slam.frontend import HammingMatcher
-    other = HammingMatcher(variant=_capi.VARIANT_POPC if a.variant == "i8" else _capi.VARIANT_I8MMA)
-    other_avg = float(np.mean(timed(lambda: other.knn2(batch), max(3, a.steps // 2), 2))) * 1e-3
-    variants_ms = {a.variant: k1_avg * 1e3, ("popc" if a.variant == "i8" else "i8"): other_avg * 1e3}
+    variants_ms = {a.variant: k1_avg * 1e3}
+    for name, vid in VARIANTS.items():
+        if name != a.variant:
+            other = HammingMatcher(variant=vid)
+            variants_ms[name] = float(np.mean(timed(lambda: other.knn2(batch), max(3, a.steps // 2), 2)))
+            del other
     popc_ops = 8.0 * float(a.pairs) * a.nfeat * a.nfeat                    # algorithmic POPC32 per launch
     alg_bytes = float(batch.total_nq + batch.total_nt) * 32 + 4.0 * (2 * batch.total_nq + batch.total_nt)
 
@@ -294,41 +299,53 @@ def b200_main(a):
     # ---- roofline denominators measured live ----
     peaks = {}
     mp_path = ROOT / "MEASURED_PEAKS.json"
-    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-    if mp_path.exists():
-        hbm_peak, hbm_src = float(json.loads(mp_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json"
-    for name in ("popc", "lop3", "imnmx", "imad", "dfma"):
+    mp = json.loads(mp_path.read_text()) if mp_path.exists() else {}
+    hbm_peak, hbm_src = float(mp.get("hbm_gbs", 6650.0)), ("MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)")
+    for name in ("popc", "lop3", "imnmx", "imad", "dfma", "shfl"):
         peaks[name] = pipe_microbench(name)
+    i8_peak = mma_microbench()                                  # dense tcgen05 kind::i8, int8 op/s
     sms, _, _, clock_khz = _devinfo(lib)
     popc_peak = peaks["popc"]
-    achieved = popc_ops / k1_avg
-    bf16_peak = float(json.loads(mp_path.read_text()).get("bf16_tflops", 1590.0)) if mp_path.exists() else 1590.0
-    i8_ops = 64.0 * popc_ops                                   # 2*256 int8 ops per descriptor pair = 64 per POPC32
-    roof_tensor = {"bound": "tensor", "achieved": i8_ops / (variants_ms["i8"] * 1e-3) / 1e12, "peak": 2.0 * bf16_peak,
-                   "unit": "TOP/s (int8)", "frac": i8_ops / (variants_ms["i8"] * 1e-3) / 1e12 / (2.0 * bf16_peak),
-                   "traffic": None, "kernel": "hamming_knn2_i8_kernel (+2 expand_pm1 launches)", "kernel_ms": variants_ms["i8"],
-                   "peak_source": "2 x measured cuBLAS bf16 (%s): no int8 GEMM peak is measured on this pool" % hbm_src,
-                   "note": "algorithmic = ONE 2*256*Nq*Nt contraction per pair; the kernel issues two (D and D^T) so that the "
-                           "column minimum is a per-thread reduction, so 0.5 is its structural ceiling"}
-    roof = {"bound": "int-popc-pipe", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
-            "frac": achieved / popc_peak, "traffic": None, "kernel": "hamming_knn2_%s_kernel" % a.variant,
-            "kernel_ms": k1_avg * 1e3, "algorithmic_popc_per_launch": popc_ops, "tensor_view": roof_tensor,
+    bf16_peak = float(mp.get("bf16_tflops", 1590.0))
+    i8_ops = 64.0 * popc_ops                                    # 2*256 int8 ops per descriptor pair = 64 per POPC32
+    shipped = "i8s" if a.variant == "popc" else a.variant
+    t_i8 = variants_ms[shipped] * 1e-3
+    # DRAM traffic of one launch of the shipped kernel, from the ncu --set full capture in profiles/
+    traffic = {"i8s": 356.2e6, "i8": 399.7e6}.get(shipped)
+    roof = {"bound": "tensor", "achieved": i8_ops / t_i8 / 1e12, "peak": i8_peak / 1e12, "unit": "TOP/s (int8)",
+            "frac": i8_ops / t_i8 / i8_peak, "traffic": traffic,
+            "kernel": {"i8s": "hamming_knn2_i8s_kernel", "i8": "hamming_knn2_i8_kernel"}[shipped] + " (+2 expand_pm8_kernel launches, timed together)",
+            "kernel_ms": variants_ms[shipped], "algorithmic_int8_ops_per_launch": i8_ops,
+            "peak_source": "b2s_mma_microbench measured in this run (dense tcgen05.mma kind::i8 M128.N128.K32 from shared memory); "
+                           "2 x MEASURED_PEAKS bf16 would be %.0f TOP/s" % (2.0 * bf16_peak),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_k2s_ncu.md",
+            "note": "algorithmic = ONE 2*256*Nq*Nt int8 contraction per frame pair (SURVEY 8d); the kernel issues 9 K-steps per 8 of "
+                    "data (the 9th adds the row/column index), and the two-product variant i8 issues the contraction twice",
             "hamming_variants_ms": variants_ms,
-            "peak_source": "b2s_pipe_microbench(popc) measured in this run: %.1f POPC/clk/SM at %d MHz max clock" % (
-                popc_peak / sms / (clock_khz * 1e3), clock_khz // 1000),
-            "hbm": {"bound": "hbm", "achieved": alg_bytes / k1_avg / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes / k1_avg / 1e9 / hbm_peak, "peak_source": hbm_src,
+            "popc_view": {"bound": "int-popc-pipe", "achieved": popc_ops / (variants_ms["popc"] * 1e-3) / 1e12, "peak": popc_peak / 1e12,
+                          "unit": "TPOPC/s", "frac": popc_ops / (variants_ms["popc"] * 1e-3) / popc_peak,
+                          "kernel": "hamming_knn2_popc_kernel", "kernel_ms": variants_ms["popc"],
+                          "note": "K1 on the integer pipe: 8 POPC32 per descriptor pair algorithmic; the carry-save tree issues 5, "
+                                  "hence > 1.  Kept as the integer-pipe baseline of the K1-vs-K2 decision."},
+            "hbm": {"bound": "hbm", "achieved": alg_bytes / t_i8 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / t_i8 / 1e9 / hbm_peak, "peak_source": hbm_src,
                     "note": "not the binding roofline: 210 POPC per byte (SURVEY 8d)"},
+            "ransac_score": {"bound": "fp64-pipe", "achieved": 20.0 * a.pairs * a.hyps * 500.0 / (stages["score"] * 1e-3) / 1e12,
+                             "peak": peaks["dfma"] / 1e12, "unit": "T fp64-pipe instr/s",
+                             "frac": 20.0 * a.pairs * a.hyps * 500.0 / (stages["score"] * 1e-3) / peaks["dfma"],
+                             "kernel": "ransac_score_kernel<double>", "kernel_ms": stages["score"],
+                             "note": "19 DFMA/DMUL + 1 DSETP per (hypothesis, correspondence), M = 500"},
             "pipe_rates_per_clk_per_sm": {k: v / sms / (clock_khz * 1e3) for k, v in peaks.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8 popcount + f64 Sampson", "data": "synthetic", "config": workload_config(a, world),
+            "dtype": "int8 (+-8 contraction of u8 bit vectors, exact) + f64 Sampson", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clk, "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": len(tracker.bounds),
                     "ms_per_step": e2e_total / a.steps},
             "stage_ms": stages, "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
-            "kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
+            "hamming_variant": a.variant,
+            "popc_kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
     if a.sweep:
         line["popc_kernel_sweep_ms"] = sweep(lib, fe, batch, timed, a)
     if world == 1 and not a.no_cpu_baseline:

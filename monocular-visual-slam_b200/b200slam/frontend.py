@@ -157,7 +157,7 @@ class HammingMatcher:
     """K1/K2 + selection.  Mirrors cv2.BFMatcher(NORM_HAMMING) knnMatch/match semantics
     (feature_pipeline.py.bak:68,82,84) on batches."""
 
-    def __init__(self, variant: int = _capi.VARIANT_POPC, t_split: int = 0):
+    def __init__(self, variant: int = _capi.VARIANT_I8MMA1, t_split: int = 0):
         self.variant = variant
         self.t_split = t_split
         self._lib = _capi.load_library()
@@ -331,7 +331,7 @@ class FrontendResult:
 class Frontend:
     """match -> select -> hypotheses -> score -> winner, all on the current stream."""
 
-    def __init__(self, cfg: FrontendConfig | None = None, variant: int = _capi.VARIANT_POPC, t_split: int = 0):
+    def __init__(self, cfg: FrontendConfig | None = None, variant: int = _capi.VARIANT_I8MMA1, t_split: int = 0):
         self.cfg = cfg or FrontendConfig()
         self.matcher = HammingMatcher(variant=variant, t_split=t_split)
         self.ransac = EssentialRansac()
@@ -361,7 +361,7 @@ class SequenceTracker:
     inlier count, and per match (compact stride max_matches) queryIdx/trainIdx/distance/inlier.
     """
 
-    def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA,
+    def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
                  chunks: int = 4, device=None):
         torch = _capi.require_cuda()
         if not cfg.max_matches:
@@ -443,6 +443,24 @@ def pipe_microbench(which: str, iters: int = 2000, ctas_per_sm: int = 8, repeats
         if r:
             best = min(best, e0.elapsed_time(e1) * 1e-3)
     return ops.value / best
+
+
+def mma_microbench(iters: int = 4000, repeats: int = 3):
+    """Measured dense tcgen05.mma kind::i8 rate (int8 op/s, 2 per MAC): every SM issues
+    M128.N128.K32 MMAs from shared memory back to back.  Roofline denominator of K2/K2s."""
+    torch = _capi.require_cuda()
+    lib = _capi.load_library()
+    macs = C.c_double(0.0)
+    best = float("inf")
+    for r in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.b2s_mma_microbench(iters, 128, C.byref(macs), current_stream()))
+        e1.record()
+        e1.synchronize()
+        if r:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return 2.0 * macs.value / best
 
 
 def unpack_keys(k: np.ndarray):

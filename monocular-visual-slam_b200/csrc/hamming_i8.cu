@@ -293,7 +293,8 @@ struct I8Params {
   uint32_t* __restrict__ bwd_best;
   int q_tiles, t_tiles, n_pairs;
   unsigned long long* dbg;  // optional per-CTA stall counters (b2s_hamming_i8_debug), else nullptr
-  int mode;                 // diagnostics only: bit 0 = epilogue does no work, bit 1 = ring is loaded once
+  int mode;                 // diagnostics only: bit 0 = epilogue does no work, bit 1 = ring is loaded once,
+                            // (single-product kernel) bit 2 = no column butterfly, bit 3 = no row top-2
 };
 // dbg layout per CTA (8 x u64): [0] MMA thread total, [1] MMA wait tempty, [2] MMA wait full/qfull,
 // [3] producer wait empty, [4] epilogue warp 2 total, [5] epilogue wait tfull, [6] tile pairs, [7] -
@@ -578,6 +579,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8_kernel(const I8
 // the MMA stream as above.
 constexpr int kI8sGo = 16;  // go barriers: the producer runs up to 8 tile pairs ahead of the MMA thread
 constexpr int kI8sQTileBytes = (kI8Chunks + 1) * kI8ChunkBytes;  // query tiles carry a zero chunk 17
+constexpr int kI8sThreads = 576;  // producer warp + MMA warp + 16 epilogue warps
 
 __device__ __forceinline__ uint32_t tc_mma_tile_single(uint32_t d, uint64_t qdesc, uint64_t tdesc, uint32_t idesc,
                                                        uint64_t* next_bar, uint32_t next_parity, uint32_t has_next) {
@@ -669,7 +671,7 @@ __device__ __forceinline__ void colmin_warp(uint32_t (&y)[64], int lane) {
   y[1] -= cfix + 0x00020002u;                                            // columns 4L+2 | 4L+3
 }
 
-__global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
+__global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_q = smem;                                   // 2 x 36 KB: sub-tile a | sub-tile b of the item (18 chunks each)
   uint8_t* s_t = smem + 2 * kI8sQTileBytes;              // kI8Stages x 34 KB
@@ -679,6 +681,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
   uint64_t* b_tfull = bars + kI8sGo + kI8Stages;         // [4] one per TMEM stage
   uint64_t* b_qempty = bars + kI8sGo + kI8Stages + 4;    // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kI8sGo + kI8Stages + 6);
+  uint2* s_merge = reinterpret_cast<uint2*>(s_tmem + 4);  // [2 item parities][2 sub-tiles][128]: the two sets of a sub-tile meet here
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_blocks = (p.q_tiles + 1) >> 1;
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
 
   // the index K-step reads one chunk past the last ring slot (times the query tile's zero chunk):
   // keep that chunk inside the allocation and defined
-  for (int i = threadIdx.x; i < kI8Tile; i += kI8Threads)
+  for (int i = threadIdx.x; i < kI8Tile; i += kI8sThreads)
     reinterpret_cast<uint4*>(s_t + kI8Stages * kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
@@ -800,12 +803,16 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
       }
     }
   } else {
-    // ===== epilogue: set = sub-tile, owning TMEM stages sub and sub+2 alternately; warp%4 = TMEM lane quarter =====
+    // ===== epilogue: 4 sets of 4 warps; set s owns TMEM stage s, i.e. the tile pairs g with g%4 == s
+    // (sub-tile s&1, every other train tile); warp%4 = TMEM lane quarter.  Four warps per scheduler
+    // instead of two: the per-tile-pair work is a long dependent chain (TMEM load, folds, butterfly)
+    // and two warps left the ALU and FMA pipes half idle. =====
     const int quarter = warp & 3;
-    const uint32_t sub = (uint32_t)(warp - 2) >> 2;
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;
+    const uint32_t sub = set & 1u;
     const int row = quarter * 32 + lane;  // TMEM lane = row of the sub-tile
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t h = 0;  // tile pairs handled by this set
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 128u;
+    uint32_t g_item = 0, hs = 0, n = 0;  // first tile pair of the item, tile pairs handled by this set, items
     long long w_tfull = 0;
     const long long e_start = p.dbg ? clock64() : 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -817,12 +824,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
       const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
       const int rows_valid = max(0, min(kI8Tile, nq - q0));
       uint32_t gbest = kNone, gsecond = kNone;
-      for (int t = 0; t < n_tt; ++t, ++h) {
-        const uint32_t g = 2u * h + sub;
+      for (int t = 0; t < n_tt; ++t) {
+        const uint32_t g = g_item + 2u * (uint32_t)t + sub;
+        if ((g & 3u) != set) continue;
         const int tbase = t * kI8Tile;
         const int nt_valid = min(kI8Tile, nt - tbase);
-        const uint32_t stage = g & 3u;
-        const uint32_t lane_addr = lane_base + stage * 128u;
         // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics)
         uint32_t cur[4];
 #pragma unroll
@@ -831,7 +837,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
           cur[k] = (c < nt_valid) ? __ldcg(&p.bwd_best[to + tbase + c]) : 0u;
         }
         const long long c0 = p.dbg ? clock64() : 0;
-        mbar_wait_bounded(&b_tfull[stage], (h >> 1) & 1u);
+        mbar_wait_bounded(&b_tfull[set], hs & 1u);
+        ++hs;
         if (p.dbg) w_tfull += clock64() - c0;
         tc_fence_after();
         if (p.mode & 1) {
@@ -840,12 +847,20 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
           if (lane == 0) mbar_arrive(&b_go[(g + 4u) % kI8sGo]);
           continue;
         }
-        uint32_t v0[32], v1[32];
-        TMEM_LD_X32P(lane_addr, v0);
-        TMEM_LD_X32P(lane_addr + 64u, v1);
-        tmem_ld_wait();
-        TMEM_REGS_READY(v0);
-        TMEM_REGS_READY(v1);
+        uint32_t y[64];
+        {
+          uint32_t v0[32], v1[32];
+          TMEM_LD_X32P(lane_addr, v0);
+          TMEM_LD_X32P(lane_addr + 64u, v1);
+          tmem_ld_wait();
+          TMEM_REGS_READY(v0);
+          TMEM_REGS_READY(v1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            y[j] = v0[j];
+            y[j + 32] = v1[j];
+          }
+        }
         tc_fence_before();
         __syncwarp();
         // accumulator drained into registers: the stage goes to tile pair g+4 (same sub-tile, two train tiles on)
@@ -856,21 +871,19 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
         // (= -(best + 1) per half-word) the wrapped sum x + c is 0xFFFF exactly for the minimum itself
         // and x - best - 1 (order preserving) for everything else; VIADDMNMX.U16x2 adds and takes
         // the running minimum in ONE instruction per register.  1.5 per register instead of 2.5.
-        {
+        if (!(p.mode & 8)) {
           uint32_t m[2] = {kNone, kNone}, a2[2] = {kNone, kNone};
-          fold_min_p16(v0, m);
-          fold_min_p16(v1, m);
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            m[0] = __vimin3_u16x2(m[0], y[j], y[j + 1]);
+            m[1] = __vimin3_u16x2(m[1], y[j + 2], y[j + 3]);
+          }
           const uint32_t bb = __vminu2(m[0], m[1]);
           const uint32_t cneg = ~bb;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            a2[0] = __viaddmin_u16x2(v0[j], cneg, a2[0]);
-            a2[1] = __viaddmin_u16x2(v0[j + 1], cneg, a2[1]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            a2[0] = __viaddmin_u16x2(v1[j], cneg, a2[0]);
-            a2[1] = __viaddmin_u16x2(v1[j + 1], cneg, a2[1]);
+          for (int j = 0; j < 64; j += 2) {
+            a2[0] = __viaddmin_u16x2(y[j], cneg, a2[0]);
+            a2[1] = __viaddmin_u16x2(y[j + 1], cneg, a2[1]);
           }
           const uint32_t ss = __vminu2(a2[0], a2[1]) + bb + 0x00010001u;  // second per 16-bit lane (no carry: < 2^16 each)
           const uint32_t bw = swap16(bb);
@@ -881,13 +894,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
           top2_insert(gbest, gsecond, key16_to_key32((sec16 & 0xFFFFu) - (uint32_t)row, (uint32_t)tbase));
         }
         // ---- column minima: butterfly over the warp on the very same registers ----
-        uint32_t y[64];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          y[j] = v0[j];
-          y[j + 32] = v1[j];
-        }
-        colmin_warp(y, lane);
+        if (!(p.mode & 4)) colmin_warp(y, lane);
         // lane L now holds columns 4L..4L+3 (y[0] = 4L | 4L+1, y[1] = 4L+2 | 4L+3) over this warp's 32 rows;
         // a candidate that does not beat the (possibly stale) current minimum needs no atomic
         const uint32_t cm16[4] = {y[0] & 0xFFFFu, y[0] >> 16, y[1] & 0xFFFFu, y[1] >> 16};
@@ -898,10 +905,20 @@ __global__ void __launch_bounds__(kI8Threads, 1) hamming_knn2_i8s_kernel(const I
           if (rows_valid > 0 && cm16[k] < kKey16Valid && key < cur[k]) atomicMin(&p.bwd_best[to + tbase + 4 * lane + k], key);
         }
       }
-      if (row < rows_valid) {
+      g_item += 2u * (uint32_t)n_tt;
+      // the two sets of a sub-tile (even / odd train tiles) meet in shared memory; double buffered by
+      // item parity, so one named barrier per item is enough
+      uint2* mg = s_merge + (((n & 1u) * 2u + sub) << 7);
+      if (set >= 2u) mg[row] = make_uint2(gbest, gsecond);
+      asm volatile("bar.sync %0, 256;" ::"r"(1u + sub) : "memory");  // the 8 warps of this sub-tile
+      if (set < 2u && row < rows_valid) {
+        const uint2 o = mg[row];
+        top2_insert(gbest, gsecond, o.x);
+        top2_insert(gbest, gsecond, o.y);
         p.fwd_best[qo + q0 + row] = gbest >= kKey32Pad ? kNone : gbest;
         p.fwd_second[qo + q0 + row] = gsecond >= kKey32Pad ? kNone : gsecond;
       }
+      ++n;
     }
     if (p.dbg && threadIdx.x == 64) {
       p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
@@ -1056,7 +1073,7 @@ constexpr size_t kI8SmemBytes =
     (size_t)(2 + kI8Stages) * kI8TileBytes + 2 * kI8ChunkBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
 constexpr size_t kI8sSmemBytes = 2 * (size_t)kI8sQTileBytes + (size_t)kI8Stages * kI8TileBytes + kI8ChunkBytes +
-                                 8 * (kI8sGo + kI8Stages + 6) + 16;
+                                 8 * (kI8sGo + kI8Stages + 6) + 16 + 4 * kI8Tile * sizeof(uint2);
 
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
@@ -1117,7 +1134,7 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
     }
     const long items = (long)((qt + 1) / 2) * n_pairs;
     const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
-    hamming_knn2_i8s_kernel<<<grid, kI8Threads, kI8sSmemBytes, st>>>(p);
+    hamming_knn2_i8s_kernel<<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
     B2S_CUDA(cudaGetLastError());
     note_launch();
     return B2S_OK;

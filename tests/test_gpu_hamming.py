@@ -16,8 +16,9 @@ def hg(golden_dir):
 
 @pytest.fixture(scope="module")
 def matcher():
+    from b200slam import _capi
     from b200slam.frontend import HammingMatcher
-    return HammingMatcher()
+    return HammingMatcher(variant=_capi.VARIANT_POPC)          # K1; the i8 variants have their own fixture below
 
 
 def _pad(a):
@@ -51,7 +52,7 @@ def test_every_kernel_configuration_is_bit_exact(hg, csa, rows, warps):
     lib = _capi.load_library()
     _capi.check(lib.b2s_hamming_set_config(csa, rows, warps))
     try:
-        m = HammingMatcher()
+        m = HammingMatcher(variant=0)
         names = ["noisy_1944x2000", "tie_w2_127x129", "orb_real_0", "duplicates_70x70", "tie_w32_300x257"]
         out = m.knn2_pairs([hg[f"{n}/q"] for n in names], [hg[f"{n}/t"] for n in names])
         for n, (fb, fs, bb) in zip(names, out):
@@ -66,7 +67,7 @@ def test_every_kernel_configuration_is_bit_exact(hg, csa, rows, warps):
 @pytest.mark.parametrize("t_split", [1, 2, 3, 7, 0])
 def test_train_split_merge_is_exact(hg, t_split):
     from b200slam.frontend import HammingMatcher
-    m = HammingMatcher(t_split=t_split)
+    m = HammingMatcher(variant=0, t_split=t_split)
     for n in ("noisy_2000x2000", "noisy_640x33", "tie_w1_300x257"):
         (fb, fs, bb), = m.knn2_pairs([hg[f"{n}/q"]], [hg[f"{n}/t"]])
         b, s, bw = ho.packed_keys(hg[f"{n}/q"], hg[f"{n}/t"])
