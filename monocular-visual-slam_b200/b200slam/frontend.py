@@ -359,10 +359,15 @@ class SequenceTracker:
     chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c (three streams).
     Results land in pinned host buffers: per pair the match count, winning hypothesis and
     inlier count, and per match (compact stride max_matches) queryIdx/trainIdx/distance/inlier.
+
+    use_graph: the whole step (uploads, ~10 launches per chunk, downloads, on three streams) is
+    captured into ONE CUDA graph on its second call with the same host buffers and replayed
+    afterwards — the eager step is bound by host launch overhead (~60 stream operations), not by
+    the device.  The caller keeps writing new frames into the same pinned staging buffers.
     """
 
     def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
-                 chunks: int = 4, device=None):
+                 chunks: int = 4, device=None, use_graph: bool = False):
         torch = _capi.require_cuda()
         if not cfg.max_matches:
             raise ValueError("SequenceTracker needs max_matches (compact output stride)")
@@ -382,11 +387,32 @@ class SequenceTracker:
                     "out_q": pin(P * S, torch.int32), "out_t": pin(P * S, torch.int32),
                     "out_d": pin(P * S, torch.int32), "mask": pin(P * S, torch.uint8)}
         self._batches = None
-        self.h2d_bytes = 0
+        self.h2d_bytes = int(self.F * frame_rows * (DESC_BYTES + 8))
         self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.out.values()))
+        self.use_graph = use_graph
+        self._graph, self._graph_key, self._eager_key = None, None, None
 
     def run(self, desc_host, kp_host, counts: np.ndarray):
         """desc_host: pinned uint8 [F*N, 32]; kp_host: pinned float32 [F*N, 2]; counts: rows used per frame."""
+        if not self.use_graph:
+            return self._run_eager(desc_host, kp_host, counts)
+        key = (desc_host.data_ptr(), kp_host.data_ptr(), np.asarray(counts).tobytes())
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+            return self.out
+        if self._eager_key != key:                                 # first call: eager (also warms every lazy init)
+            self._eager_key = key
+            return self._run_eager(desc_host, kp_host, counts)
+        torch = self.torch
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run_eager(desc_host, kp_host, counts)
+        self._graph, self._graph_key = g, key
+        g.replay()
+        return self.out
+
+    def _run_eager(self, desc_host, kp_host, counts: np.ndarray):
         torch, N = self.torch, self.N
         if self._batches is None or not np.array_equal(self._counts, counts):
             self._counts = np.array(counts, copy=True)
