@@ -163,6 +163,11 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
  * bit 1 = the operand ring is loaded once and then reused.  0 = normal operation. */
 void b2s_hamming_i8_debug(unsigned long long* dev_buf, int mode);
 
+/* Measurement: enable = 1 / 0 switches a CUDA-event pair around the tcgen05 Hamming kernel
+ * proper (without the operand pre-pass) on and off, enable < 0 leaves it as it is; if last_ms
+ * != NULL it receives the duration of the most recent timed launch (waits for it), -1 if none. */
+int b2s_hamming_kernel_timing(int enable, float* last_ms);
+
 /* Raw tcgen05.mma kind::i8 rate: every SM issues iters x 8 MMAs (M=128, N=n_dim in
  * {128,256}, K=32) from shared memory with no epilogue; *macs_out = int8 MACs issued. */
 int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream);

@@ -70,6 +70,8 @@ def _declare(lib):
     lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
     lib.b2s_hamming_i8_debug.restype = None
     lib.b2s_hamming_i8_debug.argtypes = [vp, i32]
+    lib.b2s_hamming_kernel_timing.restype = i32
+    lib.b2s_hamming_kernel_timing.argtypes = [i32, C.POINTER(C.c_float)]
     lib.b2s_mma_microbench.restype = i32
     lib.b2s_mma_microbench.argtypes = [i32, i32, C.POINTER(dbl), vp]
     lib.b2s_tmem_microbench.restype = i32
@@ -84,7 +86,7 @@ EXPORTS = (
     "b2s_hamming_knn2_batched", "b2s_hamming_set_config", "b2s_hamming_get_config",
     "b2s_select_matches", "b2s_eight_point_batched", "b2s_ransac_score_batched",
     "b2s_ransac_select", "b2s_pipe_microbench", "b2s_mma_microbench", "b2s_tmem_microbench",
-    "b2s_hamming_i8_debug",
+    "b2s_hamming_i8_debug", "b2s_hamming_kernel_timing",
 )
 
 

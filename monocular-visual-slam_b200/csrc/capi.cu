@@ -47,6 +47,7 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
                       size_t workspace_bytes, int single, cudaStream_t st);
 
 void hamming_i8_set_debug(unsigned long long* dev_buf, int mode);
+int hamming_i8_timing(int enable, float* last_ms);
 int mma_rate_launch(int iters, int n_dim, double* macs_out, cudaStream_t st);
 int tmem_read_launch(int iters, int warps, double* bytes_out, uint32_t* sink, cudaStream_t st);
 
@@ -160,6 +161,8 @@ size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int
 }
 
 void b2s_hamming_i8_debug(unsigned long long* dev_buf, int mode) { b2s::hamming_i8_set_debug(dev_buf, mode); }
+
+int b2s_hamming_kernel_timing(int enable, float* last_ms) { return b2s::hamming_i8_timing(enable, last_ms); }
 
 int b2s_mma_microbench(int iters, int n_dim, double* macs_out, void* stream) {
   return b2s::mma_rate_launch(iters, n_dim, macs_out, static_cast<cudaStream_t>(stream));
