@@ -131,7 +131,10 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
  * Replaces homography.py:328-333 for all hypotheses at once.
  * counts[p*H+h] = #{m : (x2^T E x1)^2 < th2 * (Ex1_x^2+Ex1_y^2+Etx2_x^2+Etx2_y^2)}
  * th2_per_pair: optional device array (n_pairs doubles) overriding th2.
- * precision: 64 (float64, reference arithmetic) or 32. */
+ * precision: 64 = float64 decisions (float32 screening with a rigorous rounding bound, the
+ * undecidable band re-evaluated in float64 — counts identical to 6464 at ~0.6x the time),
+ * 6464 = every evaluation in float64 (the reference's arithmetic, kept for validation),
+ * 32 = float32 only (within the north-star flip tolerance, not bit-identical). */
 int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int32_t* c_count,
                              int n_pairs, const double* E, int H, double th2,
                              const double* th2_per_pair, int precision, int32_t* counts,

@@ -73,6 +73,104 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
   if (live) counts[(size_t)pair * H + h] = count;
 }
 
+// ---- K3h: float64-exact decisions at float32 cost -----------------------------------------
+// Every (hypothesis, correspondence) is first evaluated in float32 together with a rigorous
+// bound B on what float32 rounding (of E and of the 19 operations) can have done to
+// d = num^2 - th^2 den.  |d| > B decides; only the band |d| <= B (a few per 10^5 on tracking
+// data) is re-evaluated in float64 by the same thread with the very expression of K3, so the
+// counts equal the float64 kernel's counts while the FP64 pipe (half the FP32 rate on B200, and
+// 2 issue cycles per instruction) is out of the inner loop.
+//   u = 2^-24.  With nE = ||E||_F (float32 copy), W1 = max ||x1||, W2 = max ||x2|| over the pair:
+//   |a_i - fl(a_i)| <= 4u nE W1 =: eta1, |b_j - fl(b_j)| <= 4u nE W2 =: eta2   (E rounding + 2 FMAs)
+//   |num - fl(num)| <= 8u nE W1 W2 =: delta                      (3 more roundings on |x2|.|E x1|)
+//   |den - fl(den)| <= 8u den + 4 nE (W1 eta1 + W2 eta2) + 2 (eta1^2 + eta2^2)
+//   |d - fl(d)|     <= 2 |num| delta + delta^2 + th^2 |den - fl(den)| + 4u (num^2 + th^2 den)
+// B below takes every constant 2x larger than that.
+constexpr int kScoreHThreads = 128;
+constexpr int kScoreHChunk = 1024;
+
+__global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
+    const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
+    const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp,
+    int32_t* __restrict__ counts) {
+  __shared__ float4 s_p[kScoreHChunk];
+  __shared__ float s_w[2];
+  const int pair = blockIdx.y;
+  const int h = blockIdx.x * kScoreHThreads + threadIdx.x;
+  const int M = c_count[pair];
+  const float4* cp = corr + c_off[pair];
+  const double th2d = th2_pp ? th2_pp[pair] : th2_all;
+  const float th2 = (float)th2d;
+  const bool live = h < H;
+  double ed[9];
+  float e[9];
+  float n2 = 0.0f;
+  {
+    const double* ep = E + ((size_t)pair * H + (live ? h : 0)) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      ed[k] = ep[k];
+      e[k] = (float)ed[k];
+      n2 = fmaf(e[k], e[k], n2);
+    }
+  }
+  // W1^2, W2^2 over the pair's correspondences (block reduction through shared memory)
+  if (threadIdx.x < 2) s_w[threadIdx.x] = 0.0f;
+  __syncthreads();
+  {
+    float w1 = 0.0f, w2 = 0.0f;
+    for (int m = threadIdx.x; m < M; m += kScoreHThreads) {
+      const float4 c = __ldg(cp + m);
+      w1 = fmaxf(w1, fmaf(c.x, c.x, fmaf(c.y, c.y, 1.0f)));
+      w2 = fmaxf(w2, fmaf(c.z, c.z, fmaf(c.w, c.w, 1.0f)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w1 = fmaxf(w1, __shfl_xor_sync(0xFFFFFFFFu, w1, o));
+      w2 = fmaxf(w2, __shfl_xor_sync(0xFFFFFFFFu, w2, o));
+    }
+    if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
+      atomicMax(reinterpret_cast<int*>(&s_w[0]), __float_as_int(w1));
+      atomicMax(reinterpret_cast<int*>(&s_w[1]), __float_as_int(w2));
+    }
+  }
+  __syncthreads();
+  constexpr float kU = 5.9604645e-8f * 1.0001f;                     // 2^-24, nudged up: the bound itself is rounded
+  const float nE = sqrtf(n2) * 1.0001f, W1 = sqrtf(s_w[0]) * 1.0001f, W2 = sqrtf(s_w[1]) * 1.0001f;
+  const float eta1 = 8.0f * kU * nE * W1, eta2 = 8.0f * kU * nE * W2;
+  const float delta = 16.0f * kU * nE * W1 * W2;
+  const float two_delta = 2.0f * delta;
+  const float c0 = delta * delta + th2 * (8.0f * nE * (W1 * eta1 + W2 * eta2) + 4.0f * (eta1 * eta1 + eta2 * eta2));
+  const float rho = 24.0f * kU;                                     // relative part, applied to num^2 + th^2 den
+  int count = 0;
+  for (int base = 0; base < M; base += kScoreHChunk) {
+    const int n = min(kScoreHChunk, M - base);
+    __syncthreads();
+    for (int m = threadIdx.x; m < n; m += kScoreHThreads) s_p[m] = __ldg(cp + base + m);
+    __syncthreads();
+#pragma unroll 4
+    for (int m = 0; m < n; ++m) {
+      const float4 c = s_p[m];
+      const float a0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
+      const float a1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
+      const float a2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
+      const float b0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
+      const float b1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
+      const float num = fmaf(c.z, a0, fmaf(c.w, a1, a2));
+      const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+      const float T = th2 * den;
+      const float q = num * num;
+      const float d = q - T;
+      const float B = fmaf(two_delta, fabsf(num), fmaf(rho, q + T, c0));
+      bool in = d < -B;
+      if (!(fabsf(d) > B))  // undecidable in float32 (or not finite): the float64 expression of K3 decides
+        in = sampson_inlier<double>(ed, (double)c.x, (double)c.y, (double)c.z, (double)c.w, th2d);
+      count += in ? 1 : 0;
+    }
+  }
+  if (live) counts[(size_t)pair * H + h] = count;
+}
+
 // ---- winner selection + inlier mask ---------------------------------------------------
 __global__ void __launch_bounds__(256) ransac_select_kernel(
     const int32_t* __restrict__ counts, const float4* __restrict__ corr, const int32_t* __restrict__ c_off,
@@ -373,7 +471,7 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
                              int32_t* counts, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(corr && c_off && c_count && E && counts, "null pointer");
-  B2S_REQUIRE(precision == 64 || precision == 32, "precision must be 64 or 32");
+  B2S_REQUIRE(precision == 64 || precision == 32 || precision == 6464, "precision must be 64, 32 or 6464");
   B2S_REQUIRE(n_pairs >= 0 && H >= 0, "negative size");
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (n_pairs == 0 || H == 0) return B2S_OK;
@@ -381,6 +479,8 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* c4 = reinterpret_cast<const float4*>(corr);
   if (precision == 64)
+    ransac_score_hybrid_kernel<<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
+  else if (precision == 6464)
     ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
   else
     ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);

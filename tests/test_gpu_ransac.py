@@ -157,3 +157,37 @@ def test_too_few_correspondences(R):
     from integration.pose_bridge import ransac_essential
     with pytest.raises(ValueError):
         ransac_essential(src, src, np.eye(3))
+
+
+def test_hybrid_scoring_equals_float64_everywhere(rg, R):
+    """precision=64 (float32 screening + float64 decisions inside the rounding band) must give
+    exactly the counts of precision=6464 (every evaluation in float64): golden scenes, random
+    matrices with thresholds placed ON individual residuals (forced band hits), pixel-scale
+    coordinates, tiny and huge E scales, degenerate E."""
+    import torch
+    rng = np.random.default_rng(64)
+    cases = []
+    for name in rg["names"]:
+        cases.append((rg[f"{name}/src"], rg[f"{name}/dst"], rg[f"{name}/E"].reshape(-1, 9), float(rg[f"{name}/th"])))
+    for scale, coord in ((1.0, 1.0), (1e-6, 1.0), (1e5, 1.0), (1.0, 700.0)):
+        M = 3000
+        src = (rng.uniform(-1, 1, (M, 2)) * coord).astype(np.float32)
+        dst = (src + rng.normal(0, 0.01 * coord, (M, 2))).astype(np.float32)
+        Es = rng.normal(size=(256, 9)) * scale
+        Es[0] = 0
+        Es[1] = np.array([0, 0, 0, 0, 0, 0, 0, 0, 1.0]) * scale
+        # thresholds equal to the exact residual of some correspondence under some hypothesis
+        sh, dh = np.hstack([src, np.ones((M, 1))]).astype(np.float64), np.hstack([dst, np.ones((M, 1))]).astype(np.float64)
+        with np.errstate(all="ignore"):
+            errs = ro.sampson_sq_err(Es[7].reshape(3, 3), sh, dh)
+        for th2 in (float(np.nanmedian(errs)), float(np.nanquantile(errs, 0.1)), 1e-4 * coord ** 2):
+            cases.append((src, dst, Es, float(np.sqrt(th2))))
+    total_band = 0
+    for src, dst, Es, th in cases:
+        corr, off, cnt = _dev(src, dst)
+        E = torch.from_numpy(np.ascontiguousarray(Es.reshape(1, -1, 9))).cuda()
+        c_h = R.score(corr, off, cnt, 1, E, th ** 2, precision=64).cpu().numpy()[0]
+        c_d = R.score(corr, off, cnt, 1, E, th ** 2, precision=6464).cpu().numpy()[0]
+        np.testing.assert_array_equal(c_h, c_d)
+        total_band += 1
+    assert total_band == len(cases)
