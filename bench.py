@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--variant", default="i8s", choices=["popc", "i8", "i8s"],
                     help="Hamming kernel: K1 POPC, K2 tcgen05 kind::i8 with two products, K2s single product (shipped default)")
     ap.add_argument("--chunks", type=int, default=1, help="e2e: copy/compute overlap chunks")
+    ap.add_argument("--scoring", default="cuda", choices=["tc", "cuda"], help="RANSAC scoring: K3t tensor cores or K3h CUDA cores (same counts)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="e2e: steps in flight (device/pinned buffer sets)")
     ap.add_argument("--no-graph", action="store_true", help="e2e: launch eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--sweep", action="store_true", help="also time every POPC-kernel configuration (extra key)")
@@ -172,7 +173,7 @@ def b200_main(a):
     from b200slam.frontend import SequenceTracker, sequence_batch
     desc_np, kp_np = tracking_sequence(a.pairs + 1, a.nfeat, seed=1234 + rank)
     counts = np.full(a.pairs + 1, a.nfeat, np.int32)
-    cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337 + rank)
+    cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337 + rank, scoring=a.scoring)
     VARIANTS = {"popc": _capi.VARIANT_POPC, "i8": _capi.VARIANT_I8MMA, "i8s": _capi.VARIANT_I8MMA1}
     variant = VARIANTS[a.variant]
     fe = Frontend(cfg, variant=variant)
@@ -275,7 +276,7 @@ def b200_main(a):
             sel = tm("select", lambda: fe.matcher.select(batch, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
                                                          sort_by_distance=True, max_matches=c.max_matches, with_corr=True, compact=True))
             E = tm("eight_point", lambda: fe.ransac.hypotheses(sel.corr, sel.c_off, sel.count, batch.n_pairs, c.hypotheses, seed=c.seed))
-            cnts = tm("score", lambda: fe.ransac.score(sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2, precision=c.precision))
+            cnts = tm("score", lambda: fe.score(sel, batch, E))
             tm("winner", lambda: fe.ransac.select(cnts, sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2))
         return {k: float(np.mean(v[1:])) for k, v in acc.items()}
     stages = stage_times()

@@ -140,6 +140,19 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
                              const double* th2_per_pair, int precision, int32_t* counts,
                              void* stream);
 
+/* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
+ * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
+ * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band
+ * (csrc/ransac_tc.cu).  max_m >= every c_count[p].  workspace: b2s_ransac_score_tc_workspace_bytes,
+ * 128-byte aligned.  dbg_num / dbg_den (both or neither, [pair][H][dbg_ld] float) receive the raw
+ * accumulators, dbg_band (two ints) the number of float64 re-evaluations and the work-list
+ * overflow flag; NULL in production.  Replaces the scoring lines of ransac_essential, homography.py:328-333. */
+size_t b2s_ransac_score_tc_workspace_bytes(int n_pairs, int H, int max_m);
+int b2s_ransac_score_tc(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, int max_m,
+                        const double* E, int H, double th2, const double* th2_per_pair, int32_t* counts,
+                        void* workspace, size_t workspace_bytes, float* dbg_num, float* dbg_den, int dbg_ld,
+                        int32_t* dbg_band, void* stream);
+
 /* ---- winner selection + inlier mask --------------------------------------------
  * Replaces the sequential best/early-exit bookkeeping of homography.py:335-339:
  * best_h = first h with count > 0.8*M if any, else the lowest h among the

@@ -12,25 +12,13 @@
 // The inlier test is the division-free form  num^2 < th^2 * den  of the reference's
 // num^2 / den < th^2  (den = 0 -> never an inlier in both).
 #include "common.cuh"
+#include "sampson.cuh"
 
 namespace b2s {
 
 struct Mat3 {
   double m[9];
 };
-
-// ---- Sampson test (shared by scoring and the final mask so they agree bit for bit) ----
-template <typename T>
-__device__ __forceinline__ bool sampson_inlier(const T* e, T x, T y, T u, T v, T th2) {
-  const T a0 = fma(e[0], x, fma(e[1], y, e[2]));  // (E x1)_0
-  const T a1 = fma(e[3], x, fma(e[4], y, e[5]));  // (E x1)_1
-  const T a2 = fma(e[6], x, fma(e[7], y, e[8]));  // (E x1)_2
-  const T b0 = fma(e[0], u, fma(e[3], v, e[6]));  // (E^T x2)_0
-  const T b1 = fma(e[1], u, fma(e[4], v, e[7]));  // (E^T x2)_1
-  const T num = fma(u, a0, fma(v, a1, a2));       // x2^T E x1
-  const T den = fma(a0, a0, fma(a1, a1, fma(b0, b0, b1 * b1)));
-  return num * num < th2 * den;
-}
 
 // ---- K3: one thread = one hypothesis, correspondences broadcast from shared memory ----
 constexpr int kScoreThreads = 128;
@@ -40,7 +28,8 @@ template <typename T>
 __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
     const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp,
-    int32_t* __restrict__ counts) {
+    int32_t* __restrict__ counts, const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag == 0) return;  // conditional rerun after the tensor-core pass (ransac_tc.cu)
   struct alignas(16) P4 { T x, y, u, v; };
   __shared__ P4 s_p[kScoreChunk];
   const int pair = blockIdx.y;
@@ -431,6 +420,15 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
       eo[3 * r + c] = fma(K.m[r], T1[c], fma(K.m[3 + r], T1[3 + c], K.m[6 + r] * T1[6 + c]));
 }
 
+int ransac_score_fp64_cond_launch(const float4* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
+                                  int H, double th2, const double* th2_pp, int32_t* counts, const int* run_flag, cudaStream_t st) {
+  dim3 grid((H + kScoreThreads - 1) / kScoreThreads, n_pairs);
+  ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(corr, c_off, c_count, E, H, th2, th2_pp, counts, run_flag);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
+
 }  // namespace b2s
 
 extern "C" {
@@ -481,9 +479,9 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
   if (precision == 64)
     ransac_score_hybrid_kernel<<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
   else if (precision == 6464)
-    ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
+    ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
   else
-    ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
+    ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;

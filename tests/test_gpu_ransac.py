@@ -191,3 +191,78 @@ def test_hybrid_scoring_equals_float64_everywhere(rg, R):
         np.testing.assert_array_equal(c_h, c_d)
         total_band += 1
     assert total_band == len(cases)
+
+
+def test_tensor_core_scoring_equals_float64(rg, R):
+    """K3t (tcgen05 kind::tf32, hi/lo-split operands): (1) its raw accumulators stay inside the
+    error bound the kernel assumes (kappa * ||coefficients|| * ||monomials||, measured here with a
+    4x safety factor), (2) its counts equal the all-float64 kernel's on the golden scenes, on
+    random matrices with thresholds placed on individual residuals, on pixel-scale coordinates
+    and on ragged multi-pair batches."""
+    import torch
+    rng = np.random.default_rng(65)
+    kappa = 2.0 ** -18
+
+    def exact_forms(Es, src, dst):
+        x, y, u, v = (src[:, 0].astype(np.float64), src[:, 1].astype(np.float64), dst[:, 0].astype(np.float64), dst[:, 1].astype(np.float64))
+        one = np.ones_like(x)
+        phi = np.stack([u * x, u * y, u, v * x, v * y, v, x, y, one], 1)
+        E3 = Es.reshape(-1, 3, 3)
+        num = Es.reshape(-1, 9) @ phi.T
+        x1, x2 = np.stack([x, y, one], 1), np.stack([u, v, one], 1)
+        a = np.einsum("hij,mj->hmi", E3, x1)
+        b = np.einsum("hji,mj->hmi", E3, x2)
+        den = a[..., 0] ** 2 + a[..., 1] ** 2 + b[..., 0] ** 2 + b[..., 1] ** 2
+        psi = np.stack([x * x, x * y, y * y, x, y, u * u, u * v, v * v, u, v, one], 1)
+        return num, den, np.linalg.norm(phi, axis=1).max(), np.linalg.norm(psi, axis=1).max()
+
+    cases = []
+    for name in rg["names"]:
+        cases.append((rg[f"{name}/src"], rg[f"{name}/dst"], rg[f"{name}/E"].reshape(-1, 9), float(rg[f"{name}/th"])))
+    for scale, coord, M, H in ((1.0, 1.0, 700, 300), (1e-3, 1.0, 129, 128), (1.0, 700.0, 500, 257), (50.0, 1.0, 8, 5)):
+        src = (rng.uniform(-1, 1, (M, 2)) * coord).astype(np.float32)
+        dst = (src + rng.normal(0, 0.01 * coord, (M, 2))).astype(np.float32)
+        Es = rng.normal(size=(H, 9)) * scale
+        Es[0] = 0
+        sh, dh = np.hstack([src, np.ones((M, 1))]).astype(np.float64), np.hstack([dst, np.ones((M, 1))]).astype(np.float64)
+        with np.errstate(all="ignore"):
+            errs = ro.sampson_sq_err(Es[min(7, H - 1)].reshape(3, 3), sh, dh)
+        for th2 in (float(np.nanmedian(errs)), 1e-4 * coord ** 2):
+            cases.append((src, dst, Es, float(np.sqrt(th2))))
+    worst = 0.0
+    for src, dst, Es, th in cases:
+        corr, off, cnt = _dev(src, dst)
+        E = torch.from_numpy(np.ascontiguousarray(Es.reshape(1, -1, 9))).cuda()
+        c_t, num, den, band = R.score_tc(corr, off, cnt, 1, E, th ** 2, max_m=len(src), debug=True)
+        c_d = R.score(corr, off, cnt, 1, E, th ** 2, precision=6464).cpu().numpy()[0]
+        np.testing.assert_array_equal(c_t.cpu().numpy()[0], c_d)
+        en, ed, Phi, Psi = exact_forms(Es, src, dst)
+        nE = np.linalg.norm(Es.reshape(-1, 9), axis=1)
+        E3 = Es.reshape(-1, 3, 3)
+        G = np.einsum("hka,hkb->hab", E3[:, :2, :], E3[:, :2, :])
+        Gp = np.einsum("hak,hbk->hab", E3[:, :, :2], E3[:, :, :2])
+        g = np.stack([G[:, 0, 0], 2 * G[:, 0, 1], G[:, 1, 1], 2 * G[:, 0, 2], 2 * G[:, 1, 2],
+                      Gp[:, 0, 0], 2 * Gp[:, 0, 1], Gp[:, 1, 1], 2 * Gp[:, 0, 2], 2 * Gp[:, 1, 2], G[:, 2, 2] + Gp[:, 2, 2]], 1)
+        nG = np.linalg.norm(g, axis=1)
+        with np.errstate(all="ignore"):
+            r1 = np.abs(num.cpu().numpy()[0] - en) / (kappa * nE[:, None] * Phi)
+            r2 = np.abs(den.cpu().numpy()[0] - ed) / (kappa * nG[:, None] * Psi)
+        worst = max(worst, float(np.nanmax(r1[nE > 0])), float(np.nanmax(r2[nG > 0])))
+    assert worst < 0.5, worst           # the assumed bound (kappa = 2^-18) holds with a 2x margin
+    # ragged multi-pair batch through the compact layout
+    Ms = [0, 5, 8, 130, 500, 257]
+    H = 200
+    srcs = [rng.uniform(-1, 1, (m, 2)).astype(np.float32) for m in Ms]
+    dsts = [(s + rng.normal(0, 0.02, s.shape)).astype(np.float32) for s in srcs]
+    stride = 512
+    corr = torch.zeros((len(Ms) * stride, 4), dtype=torch.float32, device="cuda")
+    for p, (s, d) in enumerate(zip(srcs, dsts)):
+        if len(s):
+            corr[p * stride:p * stride + len(s)] = torch.from_numpy(np.hstack([s, d])).cuda()
+    c_off = (torch.arange(len(Ms) + 1, dtype=torch.int32, device="cuda") * stride).contiguous()
+    c_cnt = torch.tensor(Ms, dtype=torch.int32, device="cuda")
+    E = torch.from_numpy(rng.normal(size=(len(Ms), H, 9))).cuda()
+    c_t = R.score_tc(corr, c_off, c_cnt, len(Ms), E, 0.05 ** 2, max_m=stride).cpu().numpy()
+    c_d = R.score(corr, c_off, c_cnt, len(Ms), E, 0.05 ** 2, precision=6464).cpu().numpy()
+    for p, m in enumerate(Ms):
+        np.testing.assert_array_equal(c_t[p], c_d[p], err_msg=str(m))
