@@ -360,8 +360,17 @@ def install() -> list[str]:
     bind("persistent_map", "estimate_pose_from_matches", estimate_pose_from_matches)
     bind("visual_slam_offline_entry_point", "estimate_pose_from_matches", estimate_pose_from_matches)
 
-    def _build_matcher(descriptors):                        # persistent_map.py:326-331
+    def _build_matcher(desc_a, desc_b=None):                # persistent_map.py:326-331 (called with two arrays, :262)
         return CrossCheckMatcher()
 
     bind("persistent_map", "_build_matcher", _build_matcher)
+    try:                                                    # the batched relocalizer answers with the reference's own result type
+        import persistent_map
+
+        from . import relocalization_bridge
+
+        relocalization_bridge.RelocalizationResult = persistent_map.RelocalizationResult
+        bind("persistent_map", "MapRelocalizer", relocalization_bridge.BatchedMapRelocalizer)
+    except Exception:
+        pass
     return patched
