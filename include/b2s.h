@@ -140,6 +140,25 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
                              const double* th2_per_pair, int precision, int32_t* counts,
                              void* stream);
 
+/* K5 / K6 — batched RANSAC homography (next-row #3).  Same conventions as the essential-matrix
+ * entry points: corr = (src.x, src.y, dst.x, dst.y) float32 per correspondence, CSR c_off /
+ * c_count per pair, H hypotheses per pair, H_out / Hm = [pair][H][9] float64 row-major with
+ * H[2][2] = 1 (all zero for a pair with fewer than 4 correspondences).
+ * b2s_homography_dlt_batched   replaces dlt_homography on 4-samples, homography.py:193-194 / :131-142
+ *                              (samples_in [pair][H][4] = the host's rng.choice draws, or NULL = device RNG);
+ * b2s_homography_score_batched replaces the symmetric transfer error + threshold, homography.py:196-206
+ *                              (th in the units of the points; th_per_pair optional);
+ * b2s_homography_select        replaces the strict-improvement / 0.8 n early-exit bookkeeping, :207-211,
+ *                              and writes the winner's inlier mask. */
+int b2s_homography_dlt_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, int H,
+                               const int32_t* samples_in, uint64_t seed, int32_t* samples_out, double* H_out, void* stream);
+int b2s_homography_score_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs,
+                                 const double* Hm, int H, double th, const double* th_per_pair, int32_t* counts,
+                                 void* stream);
+int b2s_homography_select(const int32_t* counts, const float* corr, const int32_t* c_off, const int32_t* c_count,
+                          int n_pairs, const double* Hm, int H, double th, const double* th_per_pair, int32_t* best_h,
+                          int32_t* best_count, uint8_t* inlier_mask, void* stream);
+
 /* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
  * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
  * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band

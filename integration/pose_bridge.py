@@ -113,6 +113,76 @@ def ransac_essential_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000,
     return [(int(best_h[p]), np.flatnonzero(mask[off[p]:off[p + 1]])) for p in range(n_pairs)]
 
 
+_hransac = None
+_hransac_pid = None
+
+
+def _device_hransac():
+    global _hransac, _hransac_pid
+    with _lock:
+        if _hransac is None or _hransac_pid != os.getpid():
+            from b200slam.frontend import HomographyRansac
+
+            _hransac = HomographyRansac()
+            _hransac_pid = os.getpid()
+        return _hransac
+
+
+def ransac_homography_batch(src_list, dst_list, th=3.0, max_iter: int = 2000, rngs=None, seed: int | None = None):
+    """Many independent ``ransac_homography`` problems (homography.py:148-216) in one set of
+    launches: K5 4-point DLT hypotheses, K6 symmetric transfer error, winner selection.
+    -> list of (best_h, inlier_index_array); best_h = -1 when nothing scored."""
+    import torch
+    from b200slam import _capi
+
+    _capi.require_cuda()
+    R = _device_hransac()
+    n_pairs = len(src_list)
+    counts_np = np.array([len(s) for s in src_list], np.int32)
+    off = np.zeros(n_pairs + 1, np.int32)
+    np.cumsum(counts_np, out=off[1:])
+    corr = np.zeros((max(int(off[-1]), 1), 4), np.float32)
+    for p, (s, d) in enumerate(zip(src_list, dst_list)):
+        corr[off[p]:off[p + 1], :2] = np.asarray(s, np.float32).reshape(-1, 2)
+        corr[off[p]:off[p + 1], 2:] = np.asarray(d, np.float32).reshape(-1, 2)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    corr_d, off_d, cnt_d = torch.from_numpy(corr).to(dev), torch.from_numpy(off).to(dev), torch.from_numpy(counts_np).to(dev)
+    samples_d = None
+    if rngs is not None:
+        smp = np.zeros((n_pairs, max_iter, 4), np.int32)
+        for p, rng in enumerate(rngs):                               # homography.py:193, same stream
+            n = int(counts_np[p])
+            if n >= 4:
+                for it in range(max_iter):
+                    smp[p, it] = rng.choice(n, 4, replace=False)
+        samples_d = torch.from_numpy(smp).to(dev)
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
+    th = np.broadcast_to(np.asarray(th, np.float64), (n_pairs,))
+    th_d = torch.from_numpy(np.array(th, dtype=np.float64)).to(dev)
+    Hm = R.hypotheses(corr_d, off_d, cnt_d, n_pairs, max_iter, samples=samples_d, seed=seed)
+    counts = R.score(corr_d, off_d, cnt_d, n_pairs, Hm, 0.0, th_per_pair=th_d)
+    best_h, best_c, mask = R.select(counts, corr_d, off_d, cnt_d, n_pairs, Hm, 0.0, th_per_pair=th_d)
+    best_h, mask = best_h.cpu().numpy(), mask.cpu().numpy()
+    return [(int(best_h[p]), np.flatnonzero(mask[off[p]:off[p + 1]])) for p in range(n_pairs)]
+
+
+def ransac_homography(src, dst, th: float = 3.0, max_iter: int = 2000, rng=None):
+    """Drop-in for homography.ransac_homography (:148-216) -> (refined H, inlier indices).
+    The hypothesis loop runs on the device; the n-point DLT refit on the winner's inliers
+    (:216) is host NumPy, once per call."""
+    from b200slam.geometry import dlt_homography_batch
+
+    src, dst = np.asarray(src, dtype=np.float64), np.asarray(dst, dtype=np.float64)
+    n = len(src)
+    if n < 4:
+        raise ValueError("At least four correspondences are required")
+    best_h, inl = ransac_homography_batch([src], [dst], th, max_iter, rngs=None if rng is None else [rng])[0]
+    if best_h < 0 or inl.size < 4:
+        raise RuntimeError("RANSAC failed — too few inliers")
+    return dlt_homography_batch(src[inl][None], dst[inl][None])[0], inl
+
+
 def ransac_essential(src, dst, K, th: float = 0.01, max_iter: int = 2000, rng=None):
     """Drop-in for homography.ransac_essential (:302-345) -> (refined E, inlier indices).
 
@@ -298,7 +368,7 @@ class RobustPoseEstimator:
         return PoseEstimate(R, _normalize_translation(t), inliers, diag)
 
     def _estimate_homography(self, pts1, pts2, K) -> PoseEstimate:
-        from b200slam.geometry import decompose_homography, ransac_homography
+        from b200slam.geometry import decompose_homography
 
         cfg = self.config
         try:
@@ -353,10 +423,11 @@ def install() -> list[str]:
             patched.append(f"{modname}.{attr}")
 
     for name, obj in (("ransac_essential", ransac_essential), ("estimate_pose_from_matches", estimate_pose_from_matches),
-                      ("match_orb_descriptors", match_orb_descriptors),
+                      ("match_orb_descriptors", match_orb_descriptors), ("ransac_homography", ransac_homography),
                       ("estimate_pose_from_orb_with_inliers", estimate_pose_from_orb_with_inliers)):
         bind("homography", name, obj)
     bind("robust_pose_estimator", "estimate_pose_from_matches", estimate_pose_from_matches)
+    bind("robust_pose_estimator", "ransac_homography", ransac_homography)
     bind("persistent_map", "estimate_pose_from_matches", estimate_pose_from_matches)
     bind("visual_slam_offline_entry_point", "estimate_pose_from_matches", estimate_pose_from_matches)
 

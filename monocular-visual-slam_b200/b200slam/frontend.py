@@ -325,6 +325,41 @@ class EssentialRansac:
         return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
 
 
+class HomographyRansac:
+    """K5 + K6 + winner selection (homography.py:148-216 batched): 4-point normalised DLT
+    hypotheses, symmetric transfer error, the reference's sequential selection rule."""
+
+    def __init__(self):
+        self._lib = _capi.load_library()
+
+    def hypotheses(self, corr, c_off, c_count, n_pairs: int, H: int, *, samples=None, seed: int = 0, return_samples: bool = False):
+        torch = _capi.require_cuda()
+        Hm = torch.empty((max(n_pairs, 1), max(H, 1), 9), dtype=torch.float64, device=corr.device)
+        s_out = torch.empty((max(n_pairs, 1), max(H, 1), 4), dtype=torch.int32, device=corr.device) if return_samples else None
+        check(self._lib.b2s_homography_dlt_batched(ptr(corr), ptr(c_off), ptr(c_count), n_pairs, H, ptr(samples),
+                                                   C.c_uint64(seed & (2**64 - 1)), ptr(s_out), ptr(Hm), current_stream()))
+        Hm = Hm[:n_pairs, :H]
+        return (Hm, s_out[:n_pairs, :H]) if return_samples else Hm
+
+    def score(self, corr, c_off, c_count, n_pairs: int, Hm, th: float, th_per_pair=None):
+        torch = _capi.require_cuda()
+        H = Hm.shape[1]
+        counts = torch.empty((max(n_pairs, 1), max(H, 1)), dtype=torch.int32, device=corr.device)
+        check(self._lib.b2s_homography_score_batched(ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(Hm), H, float(th),
+                                                     ptr(th_per_pair), ptr(counts), current_stream()))
+        return counts[:n_pairs, :H]
+
+    def select(self, counts, corr, c_off, c_count, n_pairs: int, Hm, th: float, th_per_pair=None):
+        torch = _capi.require_cuda()
+        H = Hm.shape[1]
+        best_h = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
+        best_c = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
+        mask = torch.zeros(max(corr.shape[0], 1), dtype=torch.uint8, device=corr.device)
+        check(self._lib.b2s_homography_select(ptr(counts), ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(Hm), H, float(th),
+                                              ptr(th_per_pair), ptr(best_h), ptr(best_c), ptr(mask), current_stream()))
+        return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
+
+
 @dataclass
 class FrontendConfig:
     """One pass of the hot path.  Defaults = configs/pipeline/kitti_default.json + the

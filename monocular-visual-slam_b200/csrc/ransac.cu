@@ -12,6 +12,7 @@
 // The inlier test is the division-free form  num^2 < th^2 * den  of the reference's
 // num^2 / den < th^2  (den = 0 -> never an inlier in both).
 #include "common.cuh"
+#include "linalg.cuh"
 #include "sampson.cuh"
 
 namespace b2s {
@@ -221,63 +222,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
 }
 
 // ---- K4: 8-point minimal solver, one thread per hypothesis ---------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
-  s += 0x9E3779B97F4A7C15ull;
-  uint64_t z = s;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-
-// Null vector of the 8x9 design matrix A: Householder QR of A^T (9x8, one column per sampled
-// correspondence); the last column of Q = H0 H1 ... H7 spans the orthogonal complement of the
-// rows of A.  Everything is statically indexed (registers only), there is no pivot search and no
-// select chain, and no column has to be singled out as the "free" one (for forward motion
-// E33 ~ 0, so a fixed free column would make the 8x8 system singular).  The reflector tails
-// overwrite the entries they annihilate (LAPACK storage), so the whole solve lives in the 72
-// registers of A plus 16 scalars.  The result has unit norm by construction.
-// History (us per 592k hypotheses): matrix in local memory 947 -> shared memory + complete
-// pivoting 386 -> registers + row-fixed column pivoting (select chains, 7.3k instructions per
-// hypothesis) 328 -> this version.
 constexpr int kEpThreads = 128;
-
-__device__ __forceinline__ void null_vector_8x9(double (&A)[8][9], double (&n)[9]) {
-  double v0[8], beta[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    // column k of A^T below the diagonal = A[k][k..8]
-    double s = 0.0;
-#pragma unroll
-    for (int i = k; i < 9; ++i) s = fma(A[k][i], A[k][i], s);
-    const double nrm = s * rsqrt(s);                 // sqrt(s); NaN for s = 0, masked by beta below
-    const double x0 = A[k][k];
-    v0[k] = x0 + copysign(nrm, x0);
-    beta[k] = (s > 0.0) ? 1.0 / fma(fabs(x0), nrm, s) : 0.0;  // 2 / (v^T v)
-    if (!(s > 0.0)) v0[k] = 0.0;
-#pragma unroll
-    for (int j = k + 1; j < 8; ++j) {
-      double d = v0[k] * A[j][k];
-#pragma unroll
-      for (int i = k + 1; i < 9; ++i) d = fma(A[k][i], A[j][i], d);
-      d *= beta[k];
-      A[j][k] = fma(-d, v0[k], A[j][k]);
-#pragma unroll
-      for (int i = k + 1; i < 9; ++i) A[j][i] = fma(-d, A[k][i], A[j][i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 9; ++i) n[i] = (i == 8) ? 1.0 : 0.0;
-#pragma unroll
-  for (int k = 7; k >= 0; --k) {
-    double d = v0[k] * n[k];
-#pragma unroll
-    for (int i = k + 1; i < 9; ++i) d = fma(A[k][i], n[i], d);
-    d *= beta[k];
-    n[k] = fma(-d, v0[k], n[k]);
-#pragma unroll
-    for (int i = k + 1; i < 9; ++i) n[i] = fma(-d, A[k][i], n[i]);
-  }
-}
 
 // Right-singular vector of the smallest singular value of the 3x3 matrix f (row-major).
 // cof(F) = s2 s3 u1 v1^T + s1 s3 u2 v2^T + s1 s2 u3 v3^T, so v3 is the DOMINANT eigenvector of
@@ -347,17 +292,7 @@ __global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
   if (samples_in) {
     for (int k = 0; k < 8; ++k) idx[k] = samples_in[((size_t)pair * H + h) * 8 + k];
   } else if (M >= 8) {
-    uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (uint64_t)(h + 1));
-    for (int k = 0; k < 8; ++k) {
-      int cand;
-      bool dup;
-      do {
-        cand = (int)__umul64hi(splitmix64(s), (uint64_t)M);
-        dup = false;
-        for (int a = 0; a < k; ++a) dup |= (idx[a] == cand);
-      } while (dup);
-      idx[k] = cand;
-    }
+    draw_distinct<8>(seed, pair, h, M, idx);
   } else {
     for (int k = 0; k < 8; ++k) idx[k] = 0;
   }

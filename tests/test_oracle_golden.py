@@ -154,3 +154,26 @@ def test_decompose_and_threshold(rg):
 
 def test_oracle_header_says_test_only():
     assert "TEST INFRASTRUCTURE ONLY" in oracle.__doc__
+
+
+# ---- homography branch (next-row #3) ------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def hgold(golden_dir):
+    return np.load(golden_dir / "homography_golden.npz")
+
+
+def test_homography_oracle_matches_reference(hgold):
+    from oracle import homography_oracle as hom
+    for name in hgold["names"]:
+        src, dst, th = hgold[f"{name}/src"], hgold[f"{name}/dst"], float(hgold[f"{name}/th"])
+        samples, Hs, masks, valid = hgold[f"{name}/samples"], hgold[f"{name}/H"], hgold[f"{name}/masks"], hgold[f"{name}/valid"]
+        for h in np.flatnonzero(valid):
+            H = hom.dlt_homography(src[samples[h]], dst[samples[h]])
+            np.testing.assert_allclose(H, Hs[h], rtol=1e-9, atol=1e-9, err_msg=f"{name} {h}")
+        m, c = hom.score_hypotheses(Hs[valid], src, dst, th)
+        np.testing.assert_array_equal(m, masks[valid], err_msg=name)
+        Hf, inl = hom.ransac_homography(src, dst, th=th, max_iter=len(samples), rng=np.random.default_rng(100 + int(np.flatnonzero(hgold["names"] == name)[0]) + 1))
+        np.testing.assert_array_equal(inl, hgold[f"{name}/run_inliers"], err_msg=name)
+        np.testing.assert_allclose(Hf, hgold[f"{name}/run_H"], rtol=1e-9, atol=1e-9, err_msg=name)
+        np.testing.assert_array_equal(hom.draw_samples(np.random.default_rng(100 + int(np.flatnonzero(hgold["names"] == name)[0]) + 1), len(src), len(samples)), samples)
