@@ -159,6 +159,17 @@ int b2s_homography_select(const int32_t* counts, const float* corr, const int32_
                           int n_pairs, const double* Hm, int H, double th, const double* th_per_pair, int32_t* best_h,
                           int32_t* best_count, uint8_t* inlier_mask, void* stream);
 
+/* K7 — batched decompose_essential (homography.py:251-299, next-row #2): per pair the SVD of E,
+ * the four (R, t) candidates in the reference's order (U W V^T, +u3), (U W V^T, -u3),
+ * (U W^T V^T, +u3), (U W^T V^T, -u3), and for each candidate the number of correspondences
+ * (restricted to inlier_mask != 0 when given) whose DLT triangulation lies in front of both
+ * cameras.  candidates = [pair][4][12] float64 (R row-major, then t), votes = [pair][4] int32.
+ * The caller takes the first maximum of votes (np.argmax semantics, :296-298).  K_host = 3x3
+ * row-major intrinsics on the HOST (NULL = identity); max_m >= every c_count[p]. */
+int b2s_decompose_essential_batched(const double* E, const float* corr, const int32_t* c_off, const int32_t* c_count,
+                                    const uint8_t* inlier_mask, int n_pairs, int max_m, const double* K_host,
+                                    double* candidates, int32_t* votes, void* stream);
+
 /* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
  * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
  * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band

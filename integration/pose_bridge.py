@@ -203,6 +203,40 @@ def ransac_essential(src, dst, K, th: float = 0.01, max_iter: int = 2000, rng=No
     return eight_point_refit(src[inl], dst[inl], K), inl
 
 
+def estimate_poses_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000):
+    """``ransac_essential`` + ``decompose_essential`` (homography.py:302-345, 251-299) for many
+    independent correspondence sets: ONE batched RANSAC (K4 + K3h + selection), the n-point
+    refit per set on the host, then ONE batched decomposition / cheirality vote on the device
+    (K7).  -> list of (R, t, inlier indices), or None where the reference would raise."""
+    import torch
+    from b200slam.frontend import PoseRecovery
+    from b200slam.geometry import eight_point_refit
+
+    if not src_list:
+        return []
+    res = ransac_essential_batch(src_list, dst_list, K, th=th, max_iter=max_iter)
+    ok, Es, pts = [], [], []
+    for p, (best_h, inl) in enumerate(res):
+        if best_h < 0 or inl.size < 8:
+            continue
+        s, d = np.asarray(src_list[p], np.float32)[inl], np.asarray(dst_list[p], np.float32)[inl]
+        Es.append(eight_point_refit(s, d, K).reshape(9))
+        pts.append(np.hstack([s, d]))
+        ok.append(p)
+    out = [None] * len(src_list)
+    if not ok:
+        return out
+    Ms = np.array([len(x) for x in pts], np.int32)
+    off = np.zeros(len(ok) + 1, np.int32)
+    np.cumsum(Ms, out=off[1:])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    R, t, _ = PoseRecovery().decompose(torch.from_numpy(np.stack(Es)).to(dev), torch.from_numpy(np.concatenate(pts)).to(dev),
+                                       torch.from_numpy(off).to(dev), torch.from_numpy(Ms).to(dev), len(ok), int(Ms.max()), K=K)
+    for k, p in enumerate(ok):
+        out[p] = (R[k], t[k], res[p][1])
+    return out
+
+
 def estimate_pose_from_matches(kp1, kp2, matches, K, ransac_threshold: float = 0.01, min_matches: int = 15):
     """Drop-in for homography.estimate_pose_from_matches (:423-438)."""
     from b200slam.geometry import decompose_essential

@@ -216,30 +216,16 @@ class BatchedMapRelocalizer:
 
     def _solve_poses(self, pairs):
         """estimate_pose_from_matches (homography.py:423-438) for every surviving candidate:
-        one batched RANSAC (hypotheses + scoring + winner), then refit and decomposition per
-        candidate.  -> list of (R, t, inlier indices) or None where the reference raises."""
+        one batched RANSAC (hypotheses + scoring + winner), the refit per candidate on the host and
+        one batched decomposition / cheirality vote on the device (K7).
+        -> list of (R, t, inlier indices) or None where the reference raises."""
         if not pairs:
             return []
         if self._pose_solver is not None:
             return [self._pose_solver(s, d) for s, d in pairs]
-        from b200slam.geometry import decompose_essential, eight_point_refit
+        from .pose_bridge import estimate_poses_batch
 
-        from .pose_bridge import ransac_essential_batch
-
-        res = ransac_essential_batch([s for s, _ in pairs], [d for _, d in pairs], self.intrinsics, th=self.ransac_threshold)
-        out = []
-        for (src, dst), (best_h, inl) in zip(pairs, res):
-            if best_h < 0 or inl.size < 8:
-                out.append(None)
-                continue
-            try:
-                E = eight_point_refit(src[inl], dst[inl], self.intrinsics)
-                R, t = decompose_essential(E, src[inl], dst[inl], self.intrinsics)
-            except RuntimeError:
-                out.append(None)
-                continue
-            out.append((R, t, inl))
-        return out
+        return estimate_poses_batch([s for s, _ in pairs], [d for _, d in pairs], self.intrinsics, th=self.ransac_threshold)
 
     # ---- BASELINE config #5: the whole map -------------------------------------------------
     def sweep(self, descriptors: np.ndarray, top: int = 5):

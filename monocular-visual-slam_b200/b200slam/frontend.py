@@ -325,6 +325,29 @@ class EssentialRansac:
         return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
 
 
+class PoseRecovery:
+    """K7: decompose_essential (homography.py:251-299) for many pairs in two launches — the
+    four (R, t) candidates per E and the DLT cheirality vote over the pair's inliers."""
+
+    def __init__(self):
+        self._lib = _capi.load_library()
+
+    def decompose(self, E, corr, c_off, c_count, n_pairs: int, max_m: int, mask=None, K=None):
+        """E: [n_pairs, 9] float64 device; -> (R [n_pairs,3,3], t [n_pairs,3], votes [n_pairs,4]) as
+        NumPy arrays; first maximum of the votes wins (homography.py:296-298)."""
+        torch = _capi.require_cuda()
+        dev = corr.device
+        cand = torch.empty((max(n_pairs, 1), 4, 12), dtype=torch.float64, device=dev)
+        votes = torch.empty((max(n_pairs, 1), 4), dtype=torch.int32, device=dev)
+        Kd = None if K is None else np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+        check(self._lib.b2s_decompose_essential_batched(ptr(E), ptr(corr), ptr(c_off), ptr(c_count), ptr(mask), n_pairs, int(max_m),
+                                                        ptr(Kd), ptr(cand), ptr(votes), current_stream()))
+        c, v = cand[:n_pairs].cpu().numpy(), votes[:n_pairs].cpu().numpy()
+        win = np.argmax(v, axis=1)
+        sel = c[np.arange(n_pairs), win]
+        return sel[:, :9].reshape(-1, 3, 3), sel[:, 9:], v
+
+
 class HomographyRansac:
     """K5 + K6 + winner selection (homography.py:148-216 batched): 4-point normalised DLT
     hypotheses, symmetric transfer error, the reference's sequential selection rule."""

@@ -266,3 +266,64 @@ def test_tensor_core_scoring_equals_float64(rg, R):
     c_d = R.score(corr, c_off, c_cnt, len(Ms), E, 0.05 ** 2, precision=6464).cpu().numpy()
     for p, m in enumerate(Ms):
         np.testing.assert_array_equal(c_t[p], c_d[p], err_msg=str(m))
+
+
+def test_device_decompose_essential_matches_reference(rg):
+    """K7: (R, t) of the device's decompose_essential against the reference's golden result and
+    the oracle's, and the per-candidate cheirality votes against a NumPy restatement of the vote."""
+    import torch
+    from b200slam.frontend import PoseRecovery
+    from b200slam.geometry import eight_point_refit
+    P = PoseRecovery()
+    rng = np.random.default_rng(77)
+    cases = []
+    for name in rg["names"]:
+        src, dst, K = rg[f"{name}/src"], rg[f"{name}/dst"], rg[f"{name}/K"]
+        inl = rg[f"{name}/run_s7_i2000_inl"]
+        if f"{name}/dec_R" in rg.files and len(inl) >= 8:
+            cases.append((name, src[inl], dst[inl], K, rg[f"{name}/run_s7_i2000_E"], rg[f"{name}/dec_R"], rg[f"{name}/dec_t"]))
+    assert cases
+    n_pairs = len(cases)
+    Ms = [len(c[1]) for c in cases]
+    stride = max(Ms)
+    corr = torch.zeros((n_pairs * stride, 4), dtype=torch.float32, device="cuda")
+    for p, c in enumerate(cases):
+        corr[p * stride:p * stride + Ms[p]] = torch.from_numpy(np.hstack([c[1], c[2]]).astype(np.float32)).cuda()
+    c_off = (torch.arange(n_pairs + 1, dtype=torch.int32, device="cuda") * stride).contiguous()
+    c_cnt = torch.tensor(Ms, dtype=torch.int32, device="cuda")
+    for p, (name, src, dst, K, E, Rw, tw) in enumerate(cases):
+        # one pair at a time (K differs between the scenes)
+        R, t, votes = P.decompose(torch.from_numpy(np.ascontiguousarray(E.reshape(1, 9))).cuda(), corr[p * stride:], c_off[:2] * 0 + torch.tensor([0, stride], dtype=torch.int32, device="cuda"),
+                                  c_cnt[p:p + 1], 1, stride, K=K)
+        Ro, to = ro.decompose_essential(E, src, dst, K)
+        np.testing.assert_allclose(R[0], Ro, atol=1e-8, err_msg=name)
+        np.testing.assert_allclose(t[0], to, atol=1e-8, err_msg=name)
+        if Rw.shape == (3, 3):
+            np.testing.assert_allclose(R[0], Rw, atol=1e-8, err_msg=name)
+            np.testing.assert_allclose(t[0], tw, atol=1e-8, err_msg=name)
+        assert votes[0].max() > 0 and votes[0].sum() <= 4 * len(src), (name, votes)
+    # batched, with inlier masks, identity intrinsics: votes equal a NumPy DLT vote on every candidate
+    n_pairs, M = 5, 200
+    Es, srcs, dsts, masks = [], [], [], []
+    for p in range(n_pairs):
+        Pw = np.stack([rng.uniform(-3, 3, M), rng.uniform(-2, 2, M), rng.uniform(4, 20, M)], axis=1)
+        yaw = rng.uniform(-0.1, 0.1)
+        Rt = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        tt = rng.normal(size=3)
+        tt /= np.linalg.norm(tt)
+        P2 = Pw @ Rt.T + tt
+        s = (Pw[:, :2] / Pw[:, 2:]).astype(np.float32)
+        d = (P2[:, :2] / P2[:, 2:] + rng.normal(0, 1e-3, (M, 2))).astype(np.float32)
+        mk = (rng.random(M) < 0.7).astype(np.uint8)
+        Es.append(eight_point_refit(s[mk > 0], d[mk > 0], np.eye(3)).reshape(9))
+        srcs.append(s), dsts.append(d), masks.append(mk)
+    corr = torch.from_numpy(np.hstack([np.concatenate(srcs), np.concatenate(dsts)])).cuda()
+    c_off = (torch.arange(n_pairs + 1, dtype=torch.int32, device="cuda") * M).contiguous()
+    c_cnt = torch.full((n_pairs,), M, dtype=torch.int32, device="cuda")
+    R, t, votes = P.decompose(torch.from_numpy(np.stack(Es)).cuda(), corr, c_off, c_cnt, n_pairs, M, mask=torch.from_numpy(np.concatenate(masks)).cuda())
+    for p in range(n_pairs):
+        mk = masks[p] > 0
+        Ro, to = ro.decompose_essential(Es[p].reshape(3, 3), srcs[p][mk], dsts[p][mk], np.eye(3))
+        np.testing.assert_allclose(R[p], Ro, atol=1e-8)
+        np.testing.assert_allclose(t[p], to, atol=1e-8)
+        assert votes[p].max() >= 0.95 * mk.sum() and np.sort(votes[p])[-2] < 0.5 * mk.sum()
