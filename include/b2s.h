@@ -170,6 +170,13 @@ int b2s_decompose_essential_batched(const double* E, const float* corr, const in
                                     const uint8_t* inlier_mask, int n_pairs, int max_m, const double* K_host,
                                     double* candidates, int32_t* votes, void* stream);
 
+/* Refit of E on a pair's inliers (homography.py:344 -> eight_point_E, :222-248, K^T F K quirk
+ * included): E_out [pair][9] float64 (zeros when fewer than 8 correspondences take part),
+ * n_used [pair] (optional) = correspondences that took part.  inlier_mask NULL = all. */
+int b2s_refit_essential_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, const uint8_t* inlier_mask,
+                                int n_pairs, const double* K_host, const double* Kinv_host, double* E_out, int32_t* n_used,
+                                void* stream);
+
 /* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
  * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
  * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band

@@ -205,35 +205,38 @@ def ransac_essential(src, dst, K, th: float = 0.01, max_iter: int = 2000, rng=No
 
 def estimate_poses_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000):
     """``ransac_essential`` + ``decompose_essential`` (homography.py:302-345, 251-299) for many
-    independent correspondence sets: ONE batched RANSAC (K4 + K3h + selection), the n-point
-    refit per set on the host, then ONE batched decomposition / cheirality vote on the device
-    (K7).  -> list of (R, t, inlier indices), or None where the reference would raise."""
+    independent correspondence sets, everything on the device: ONE batched RANSAC (K4 + K3h +
+    selection), ONE batched n-point refit on the winners' inliers, ONE batched decomposition /
+    cheirality vote (K7).  -> list of (R, t, inlier indices), or None where the reference would raise."""
     import torch
     from b200slam.frontend import PoseRecovery
-    from b200slam.geometry import eight_point_refit
 
-    if not src_list:
+    n_pairs = len(src_list)
+    if n_pairs == 0:
         return []
     res = ransac_essential_batch(src_list, dst_list, K, th=th, max_iter=max_iter)
-    ok, Es, pts = [], [], []
-    for p, (best_h, inl) in enumerate(res):
-        if best_h < 0 or inl.size < 8:
-            continue
-        s, d = np.asarray(src_list[p], np.float32)[inl], np.asarray(dst_list[p], np.float32)[inl]
-        Es.append(eight_point_refit(s, d, K).reshape(9))
-        pts.append(np.hstack([s, d]))
-        ok.append(p)
-    out = [None] * len(src_list)
-    if not ok:
-        return out
-    Ms = np.array([len(x) for x in pts], np.int32)
-    off = np.zeros(len(ok) + 1, np.int32)
+    Ms = np.array([len(s) for s in src_list], np.int32)
+    off = np.zeros(n_pairs + 1, np.int32)
     np.cumsum(Ms, out=off[1:])
+    corr = np.zeros((max(int(off[-1]), 1), 4), np.float32)
+    mask = np.zeros(max(int(off[-1]), 1), np.uint8)
+    ok = np.zeros(n_pairs, bool)
+    for p, (best_h, inl) in enumerate(res):
+        corr[off[p]:off[p + 1], :2] = np.asarray(src_list[p], np.float32).reshape(-1, 2)
+        corr[off[p]:off[p + 1], 2:] = np.asarray(dst_list[p], np.float32).reshape(-1, 2)
+        if best_h >= 0 and inl.size >= 8:
+            mask[off[p] + inl] = 1
+            ok[p] = True
+    out = [None] * n_pairs
+    if not ok.any():
+        return out
     dev = torch.device("cuda", torch.cuda.current_device())
-    R, t, _ = PoseRecovery().decompose(torch.from_numpy(np.stack(Es)).to(dev), torch.from_numpy(np.concatenate(pts)).to(dev),
-                                       torch.from_numpy(off).to(dev), torch.from_numpy(Ms).to(dev), len(ok), int(Ms.max()), K=K)
-    for k, p in enumerate(ok):
-        out[p] = (R[k], t[k], res[p][1])
+    corr_d, off_d, cnt_d, mask_d = (torch.from_numpy(x).to(dev) for x in (corr, off, Ms, mask))
+    P = PoseRecovery()
+    E, _ = P.refit(corr_d, off_d, cnt_d, n_pairs, mask=mask_d, K=K)
+    R, t, _ = P.decompose(E, corr_d, off_d, cnt_d, n_pairs, int(Ms.max()), mask=mask_d, K=K)
+    for p in np.flatnonzero(ok):
+        out[p] = (R[p], t[p], res[p][1])
     return out
 
 

@@ -332,6 +332,19 @@ class PoseRecovery:
     def __init__(self):
         self._lib = _capi.load_library()
 
+    def refit(self, corr, c_off, c_count, n_pairs: int, mask=None, K=None):
+        """n-point E on each pair's inliers (homography.py:344) -> (E [n_pairs, 9] float64 device, n_used device)."""
+        torch = _capi.require_cuda()
+        E = torch.empty((max(n_pairs, 1), 9), dtype=torch.float64, device=corr.device)
+        used = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
+        Kd = Kinv = None
+        if K is not None:
+            Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+            Kinv = np.ascontiguousarray(np.linalg.inv(Kd))
+        check(self._lib.b2s_refit_essential_batched(ptr(corr), ptr(c_off), ptr(c_count), ptr(mask), n_pairs, ptr(Kd), ptr(Kinv),
+                                                    ptr(E), ptr(used), current_stream()))
+        return E[:n_pairs], used[:n_pairs]
+
     def decompose(self, E, corr, c_off, c_count, n_pairs: int, max_m: int, mask=None, K=None):
         """E: [n_pairs, 9] float64 device; -> (R [n_pairs,3,3], t [n_pairs,3], votes [n_pairs,4]) as
         NumPy arrays; first maximum of the votes wins (homography.py:296-298)."""

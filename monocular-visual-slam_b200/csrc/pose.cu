@@ -263,3 +263,172 @@ int b2s_decompose_essential_batched(const double* E, const float* corr, const in
 }
 
 }  // extern "C"
+
+// ---- n-point refit of E on the winner's inliers (homography.py:344 -> eight_point_E :222-248) ----
+#include "linalg.cuh"
+
+namespace b2s {
+
+constexpr int kRefitThreads = 256;
+
+// One CTA per pair.  The design matrix A (n x 9, one row per inlier) is never formed: its Gram
+// matrix A^T A (9x9) is accumulated in a fixed order (per-thread partial sums over a strided
+// subset, warp shuffles, then the 8 warps in warp order: deterministic), and the right-singular
+// vector of A's smallest singular value is the eigenvector of the smallest eigenvalue of A^T A,
+// found by a warp-cooperative cyclic Jacobi in shared memory.  Rank-2 projection and K^T F K as
+// in the minimal solver.
+__global__ void __launch_bounds__(kRefitThreads) refit_essential_kernel(
+    const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
+    const uint8_t* __restrict__ mask, const PoseMat3 K, const PoseMat3 Kinv, double* __restrict__ E_out,
+    int32_t* __restrict__ n_used) {
+  __shared__ double s_part[8][45];
+  __shared__ double s_M[9][9], s_V[9][9];
+  __shared__ double s_cs[2];
+  __shared__ int s_n[8];
+  const int pair = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = c_count[pair];
+  const float4* cp = corr + c_off[pair];
+  const uint8_t* mp = mask ? mask + c_off[pair] : nullptr;
+  double acc[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+  int n = 0;
+  const double* ki = Kinv.m;
+  for (int m = tid; m < M; m += kRefitThreads) {
+    if (mp && mp[m] == 0) continue;
+    const float4 c = cp[m];
+    const double sx = c.x, sy = c.y, dx = c.z, dy = c.w;
+    const double w1 = fma(ki[6], sx, fma(ki[7], sy, ki[8])), w2 = fma(ki[6], dx, fma(ki[7], dy, ki[8]));
+    const double x = fma(ki[0], sx, fma(ki[1], sy, ki[2])) / w1, y = fma(ki[3], sx, fma(ki[4], sy, ki[5])) / w1;
+    const double u = fma(ki[0], dx, fma(ki[1], dy, ki[2])) / w2, v = fma(ki[3], dx, fma(ki[4], dy, ki[5])) / w2;
+    const double a[9] = {u * x, u * y, u, v * x, v * y, v, x, y, 1.0};
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int j = i; j < 9; ++j) acc[k] = fma(a[i], a[j], acc[k]), ++k;
+    ++n;
+  }
+#pragma unroll
+  for (int k = 0; k < 45; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xFFFFFFFFu, acc[k], o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 45; ++k) s_part[warp][k] = acc[k];
+    s_n[warp] = n;
+  }
+  __syncthreads();
+  if (tid < 45) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w][tid];
+    // unpack the upper triangle index tid -> (i, j)
+    int i = 0, rem = tid;
+    while (rem >= 9 - i) rem -= 9 - i, ++i;
+    const int j = i + rem;
+    s_M[i][j] = t;
+    s_M[j][i] = t;
+  }
+  if (tid < 81) s_V[tid / 9][tid % 9] = (tid / 9 == tid % 9) ? 1.0 : 0.0;
+  __syncthreads();
+  if (warp != 0) return;
+  int total = 0;
+  for (int w = 0; w < 8; ++w) total += s_n[w];
+  if (lane == 0 && n_used) n_used[pair] = total;
+  double* eo = E_out + (size_t)pair * 9;
+  if (total < 8) {
+    if (lane < 9) eo[lane] = 0.0;
+    return;
+  }
+  // cyclic Jacobi on the 9x9 Gram matrix, warp-cooperative: lane k < 9 owns index k of the rotated rows / columns
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+    if (lane < 9)
+      for (int j = 0; j < 9; ++j) off += (j != lane) ? fabs(s_M[lane][j]) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xFFFFFFFFu, off, o);
+    double diag = (lane < 9) ? fabs(s_M[lane][lane]) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xFFFFFFFFu, diag, o);
+    if (off <= 1e-22 * diag) break;
+    for (int p = 0; p < 8; ++p)
+      for (int q = p + 1; q < 9; ++q) {
+        if (lane == 0) {
+          const double apq = s_M[p][q];
+          double c = 1.0, s = 0.0;
+          if (apq != 0.0) {
+            const double theta = (s_M[q][q] - s_M[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            c = rsqrt(fma(t, t, 1.0));
+            s = t * c;
+          }
+          s_cs[0] = c;
+          s_cs[1] = s;
+        }
+        __syncwarp();
+        const double c = s_cs[0], s = s_cs[1];
+        if (lane < 9) {  // M <- M J (columns p, q), V <- V J
+          const double mkp = s_M[lane][p], mkq = s_M[lane][q];
+          s_M[lane][p] = c * mkp - s * mkq;
+          s_M[lane][q] = s * mkp + c * mkq;
+          const double vkp = s_V[lane][p], vkq = s_V[lane][q];
+          s_V[lane][p] = c * vkp - s * vkq;
+          s_V[lane][q] = s * vkp + c * vkq;
+        }
+        __syncwarp();
+        if (lane < 9) {  // M <- J^T M (rows p, q)
+          const double mpk = s_M[p][lane], mqk = s_M[q][lane];
+          s_M[p][lane] = c * mpk - s * mqk;
+          s_M[q][lane] = s * mpk + c * mqk;
+        }
+        __syncwarp();
+      }
+  }
+  if (lane == 0) {
+    int best = 0;
+    for (int k = 1; k < 9; ++k) best = (s_M[k][k] < s_M[best][best]) ? k : best;
+    double f[9];
+    for (int k = 0; k < 9; ++k) f[k] = s_V[k][best];
+    double v3[3];
+    smallest_right_singular3(f, v3);
+    double Fp[9];
+    for (int r = 0; r < 3; ++r) {
+      const double fv = fma(f[3 * r], v3[0], fma(f[3 * r + 1], v3[1], f[3 * r + 2] * v3[2]));
+      for (int c = 0; c < 3; ++c) Fp[3 * r + c] = fma(-fv, v3[c], f[3 * r + c]);
+    }
+    double T1[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) T1[3 * r + c] = fma(Fp[3 * r], K.m[c], fma(Fp[3 * r + 1], K.m[3 + c], Fp[3 * r + 2] * K.m[6 + c]));
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) eo[3 * r + c] = fma(K.m[r], T1[c], fma(K.m[3 + r], T1[3 + c], K.m[6 + r] * T1[6 + c]));
+  }
+}
+
+}  // namespace b2s
+
+extern "C" {
+
+int b2s_refit_essential_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, const uint8_t* inlier_mask,
+                                int n_pairs, const double* K_host, const double* Kinv_host, double* E_out, int32_t* n_used,
+                                void* stream) {
+  using namespace b2s;
+  B2S_REQUIRE(corr && c_off && c_count && E_out, "null pointer");
+  B2S_REQUIRE(n_pairs >= 0, "negative size");
+  B2S_REQUIRE((K_host == nullptr) == (Kinv_host == nullptr), "pass both K and Kinv or neither");
+  if (n_pairs == 0) return B2S_OK;
+  PoseMat3 K, Kinv;
+  for (int i = 0; i < 9; ++i) {
+    K.m[i] = K_host ? K_host[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+    Kinv.m[i] = Kinv_host ? Kinv_host[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+  }
+  refit_essential_kernel<<<n_pairs, kRefitThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(corr), c_off, c_count, inlier_mask, K, Kinv, E_out, n_used);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
+
+}  // extern "C"

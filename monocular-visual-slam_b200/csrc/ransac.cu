@@ -224,57 +224,6 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
 // ---- K4: 8-point minimal solver, one thread per hypothesis ---------------------------
 constexpr int kEpThreads = 128;
 
-// Right-singular vector of the smallest singular value of the 3x3 matrix f (row-major).
-// cof(F) = s2 s3 u1 v1^T + s1 s3 u2 v2^T + s1 s2 u3 v3^T, so v3 is the DOMINANT eigenvector of
-// M = cof(F)^T cof(F) with eigenvalue ratio (s3/s2)^2; repeated squaring of the trace-normalised
-// M squares that ratio every step.  With tr(M) = 1 the trace of M^2 is 1 - 2*delta (delta = the
-// second eigenvalue), so the loop stops after the squaring that saw delta < 1e-8: its result is
-// rank one to 1e-16.  3-6 squarings for well-posed samples, 12+ only when s3/s2 > 0.99.
-// No division, square root or trigonometry inside the loop (the cyclic Jacobi solver this
-// replaces spent ~5k instructions per hypothesis on them).
-__device__ __forceinline__ void smallest_right_singular3(const double (&f)[9], double (&v)[3]) {
-  double c[9];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-      c[3 * i + j] = fma(f[3 * i1 + j1], f[3 * i2 + j2], -f[3 * i1 + j2] * f[3 * i2 + j1]);
-    }
-  // symmetric M: m00 m01 m02 m11 m12 m22
-  double m00 = fma(c[0], c[0], fma(c[3], c[3], c[6] * c[6]));
-  double m01 = fma(c[0], c[1], fma(c[3], c[4], c[6] * c[7]));
-  double m02 = fma(c[0], c[2], fma(c[3], c[5], c[6] * c[8]));
-  double m11 = fma(c[1], c[1], fma(c[4], c[4], c[7] * c[7]));
-  double m12 = fma(c[1], c[2], fma(c[4], c[5], c[7] * c[8]));
-  double m22 = fma(c[2], c[2], fma(c[5], c[5], c[8] * c[8]));
-  for (int it = 0; it < 40; ++it) {
-    const double tr = m00 + m11 + m22;
-    if (!(tr > 0.0)) break;                          // cof(F) = 0: F has rank <= 1, nothing to project
-    const double inv = 1.0 / tr;
-    m00 *= inv; m01 *= inv; m02 *= inv; m11 *= inv; m12 *= inv; m22 *= inv;
-    const double n00 = fma(m00, m00, fma(m01, m01, m02 * m02));
-    const double n01 = fma(m00, m01, fma(m01, m11, m02 * m12));
-    const double n02 = fma(m00, m02, fma(m01, m12, m02 * m22));
-    const double n11 = fma(m01, m01, fma(m11, m11, m12 * m12));
-    const double n12 = fma(m01, m02, fma(m11, m12, m12 * m22));
-    const double n22 = fma(m02, m02, fma(m12, m12, m22 * m22));
-    m00 = n00; m01 = n01; m02 = n02; m11 = n11; m12 = n12; m22 = n22;
-    if (1.0 - (n00 + n11 + n22) < 2e-8) break;
-  }
-  // the column with the largest diagonal entry is the best-conditioned copy of v3
-  const bool use1 = m11 > m00;
-  const double d01 = use1 ? m11 : m00;
-  const bool use2 = m22 > d01;
-  const double a = use2 ? m02 : (use1 ? m01 : m00);
-  const double b = use2 ? m12 : (use1 ? m11 : m01);
-  const double g = use2 ? m22 : (use1 ? m12 : m02);
-  const double r = rsqrt(fma(a, a, fma(b, b, g * g)));
-  v[0] = a * r;
-  v[1] = b * r;
-  v[2] = g * r;
-}
-
 // AFFINE: the last row of Kinv is (0 0 1), so the dehomogenising divisions are by exactly 1.
 // KEYE: K = I, so the K^T F K product is the identity map.  Both are decided on the host.
 template <bool AFFINE, bool KEYE>

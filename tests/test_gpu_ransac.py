@@ -327,3 +327,31 @@ def test_device_decompose_essential_matches_reference(rg):
         np.testing.assert_allclose(R[p], Ro, atol=1e-8)
         np.testing.assert_allclose(t[p], to, atol=1e-8)
         assert votes[p].max() >= 0.95 * mk.sum() and np.sort(votes[p])[-2] < 0.5 * mk.sum()
+
+
+def test_device_refit_matches_reference_runs(rg):
+    """Refit of E on the winner's inliers (homography.py:344): the device's Gram-matrix + Jacobi
+    solution against the refined E the unmodified reference returned for its seeded runs."""
+    import torch
+    from b200slam.frontend import PoseRecovery
+    P = PoseRecovery()
+    checked = 0
+    for name in rg["names"]:
+        src, dst, K = rg[f"{name}/src"], rg[f"{name}/dst"], rg[f"{name}/K"]
+        for run in ("run_s7_i2000", "run_s8_i2000", "run_s9_i25"):
+            if not bool(rg[f"{name}/{run}_ok"]):
+                continue
+            inl, Eref = rg[f"{name}/{run}_inl"], rg[f"{name}/{run}_E"]
+            mask = np.zeros(len(src), np.uint8)
+            mask[inl] = 1
+            corr, off, cnt = _dev(src, dst)
+            E, used = P.refit(corr, off, cnt, 1, mask=torch.from_numpy(mask).cuda(), K=K)
+            assert int(used[0]) == len(inl)
+            a, b = _align(E[0].cpu().numpy().reshape(3, 3), Eref)
+            np.testing.assert_allclose(a, b, atol=1e-8, err_msg=f"{name} {run}")
+            checked += 1
+    assert checked >= 8
+    # fewer than 8 inliers -> zeros, like the guard of eight_point_E (:224-225) would stop the reference
+    corr, off, cnt = _dev(src[:5], dst[:5])
+    E, used = P.refit(corr, off, cnt, 1)
+    assert int(used[0]) == 5 and (E.cpu().numpy() == 0).all()
