@@ -260,6 +260,9 @@ def b200_main(a):
     alg_bytes = float(batch.total_nq + batch.total_nt) * 32 + 4.0 * (2 * batch.total_nq + batch.total_nt)
 
     # ---- per-stage device times (CUDA events around each C-ABI call, same inputs) ----
+    from b200slam.frontend import PoseRecovery
+    pose_rec = PoseRecovery()
+
     def stage_times(reps=5):
         c = fe.cfg
         acc = {}
@@ -277,7 +280,9 @@ def b200_main(a):
                                                          sort_by_distance=True, max_matches=c.max_matches, with_corr=True, compact=True))
             E = tm("eight_point", lambda: fe.ransac.hypotheses(sel.corr, sel.c_off, sel.count, batch.n_pairs, c.hypotheses, seed=c.seed))
             cnts = tm("score", lambda: fe.score(sel, batch, E))
-            tm("winner", lambda: fe.ransac.select(cnts, sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2))
+            w = tm("winner", lambda: fe.ransac.select(cnts, sel.corr, sel.c_off, sel.count, batch.n_pairs, E, c.threshold ** 2))
+            if pose_rec is not None:     # not part of the metric's unit: reported beside it
+                tm("pose_recovery_extra", lambda: pose_rec.recover(sel.corr, sel.c_off, sel.count, batch.n_pairs, sel.stride, mask=w[2]))
         return {k: float(np.mean(v[1:])) for k, v in acc.items()}
     stages = stage_times()
 

@@ -170,6 +170,10 @@ int b2s_decompose_essential_batched(const double* E, const float* corr, const in
                                     const uint8_t* inlier_mask, int n_pairs, int max_m, const double* K_host,
                                     double* candidates, int32_t* votes, void* stream);
 
+/* The (R, t) of the first candidate with the most votes (np.argmax semantics of homography.py:296-298):
+ * R_out [pair][9], t_out [pair][3] float64. */
+int b2s_pose_pick(const double* candidates, const int32_t* votes, int n_pairs, double* R_out, double* t_out, void* stream);
+
 /* Refit of E on a pair's inliers (homography.py:344 -> eight_point_E, :222-248, K^T F K quirk
  * included): E_out [pair][9] float64 (zeros when fewer than 8 correspondences take part),
  * n_used [pair] (optional) = correspondences that took part.  inlier_mask NULL = all. */

@@ -345,6 +345,22 @@ class PoseRecovery:
                                                     ptr(E), ptr(used), current_stream()))
         return E[:n_pairs], used[:n_pairs]
 
+    def recover(self, corr, c_off, c_count, n_pairs: int, max_m: int, mask=None, K=None):
+        """refit + decompose + pick, all on the current stream, nothing copied to the host:
+        -> (E [n,9], R [n,9], t [n,3], votes [n,4]) device tensors."""
+        torch = _capi.require_cuda()
+        dev = corr.device
+        E, _ = self.refit(corr, c_off, c_count, n_pairs, mask=mask, K=K)
+        cand = torch.empty((max(n_pairs, 1), 4, 12), dtype=torch.float64, device=dev)
+        votes = torch.empty((max(n_pairs, 1), 4), dtype=torch.int32, device=dev)
+        R = torch.empty((max(n_pairs, 1), 9), dtype=torch.float64, device=dev)
+        t = torch.empty((max(n_pairs, 1), 3), dtype=torch.float64, device=dev)
+        Kd = None if K is None else np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+        check(self._lib.b2s_decompose_essential_batched(ptr(E), ptr(corr), ptr(c_off), ptr(c_count), ptr(mask), n_pairs, int(max_m),
+                                                        ptr(Kd), ptr(cand), ptr(votes), current_stream()))
+        check(self._lib.b2s_pose_pick(ptr(cand), ptr(votes), n_pairs, ptr(R), ptr(t), current_stream()))
+        return E, R[:n_pairs], t[:n_pairs], votes[:n_pairs]
+
     def decompose(self, E, corr, c_off, c_count, n_pairs: int, max_m: int, mask=None, K=None):
         """E: [n_pairs, 9] float64 device; -> (R [n_pairs,3,3], t [n_pairs,3], votes [n_pairs,4]) as
         NumPy arrays; first maximum of the votes wins (homography.py:296-298)."""
@@ -408,6 +424,7 @@ class FrontendConfig:
     threshold: float = 0.01
     precision: int = 64
     seed: int = 1337
+    with_pose: bool = False    # also refit E on the winner's inliers and recover (R, t) on the device (K7)
     scoring: str = "cuda"      # "cuda": K3h on the CUDA cores (default); "tc": K3t tensor-core scoring.  Same counts; K3t is 8 %
                                # faster alone but, as a second 220 KB-shared-memory persistent kernel, overlaps worse with K2s
                                # when two steps are in flight (bench e2e 281k vs 326k pairs/s)
@@ -422,6 +439,10 @@ class FrontendResult:
     best_h: "torch.Tensor"
     best_count: "torch.Tensor"
     inlier_mask: "torch.Tensor"
+    E_refit: "torch.Tensor | None" = None
+    R: "torch.Tensor | None" = None
+    t: "torch.Tensor | None" = None
+    votes: "torch.Tensor | None" = None
 
 
 class Frontend:
@@ -431,6 +452,7 @@ class Frontend:
         self.cfg = cfg or FrontendConfig()
         self.matcher = HammingMatcher(variant=variant, t_split=t_split)
         self.ransac = EssentialRansac()
+        self.pose = None
         self.launches_per_run = 0
 
     def score(self, sel: Selection, b: PairBatch, E):
@@ -451,7 +473,13 @@ class Frontend:
         th2 = c.threshold ** 2
         counts = self.score(sel, b, E)
         best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
-        return FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
+        res = FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
+        if c.with_pose:      # next-row #2: refit on the winner's inliers + decomposition / cheirality vote (K7)
+            if self.pose is None:
+                self.pose = PoseRecovery()
+            res.E_refit, res.R, res.t, res.votes = self.pose.recover(sel.corr, sel.c_off, sel.count, b.n_pairs,
+                                                                      sel.stride or b.max_nq, mask=mask, K=K)
+        return res
 
 
 class SequenceTracker:

@@ -234,9 +234,31 @@ __global__ void __launch_bounds__(128) cheirality_vote_kernel(const float4* __re
   }
 }
 
+// first maximum of the four votes wins (homography.py:296-298)
+__global__ void __launch_bounds__(64) pose_pick_kernel(const double* __restrict__ cand, const int32_t* __restrict__ votes,
+                                                       int n_pairs, double* __restrict__ R_out, double* __restrict__ t_out) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  int win = 0;
+  for (int c = 1; c < 4; ++c) win = (votes[pair * 4 + c] > votes[pair * 4 + win]) ? c : win;
+  const double* o = cand + (size_t)pair * 48 + win * 12;
+  for (int k = 0; k < 9; ++k) R_out[(size_t)pair * 9 + k] = o[k];
+  for (int k = 0; k < 3; ++k) t_out[(size_t)pair * 3 + k] = o[9 + k];
+}
+
 }  // namespace b2s
 
 extern "C" {
+
+int b2s_pose_pick(const double* candidates, const int32_t* votes, int n_pairs, double* R_out, double* t_out, void* stream) {
+  using namespace b2s;
+  B2S_REQUIRE(candidates && votes && R_out && t_out, "null pointer");
+  if (n_pairs <= 0) return B2S_OK;
+  pose_pick_kernel<<<(n_pairs + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(candidates, votes, n_pairs, R_out, t_out);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
 
 int b2s_decompose_essential_batched(const double* E, const float* corr, const int32_t* c_off, const int32_t* c_count,
                                     const uint8_t* inlier_mask, int n_pairs, int max_m, const double* K_host,

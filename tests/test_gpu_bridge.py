@@ -139,3 +139,33 @@ def test_sequence_tracker_equals_independent_pairs():
             np.testing.assert_array_equal(out["out_d"][p * 300:p * 300 + c].numpy(), d)
             assert int(out["best_count"][p]) == int(out["mask"][p * 300:p * 300 + c].sum())
             assert int(out["best_count"][p]) > 0.5 * c          # the planted motion is found
+
+
+def test_frontend_with_pose_recovers_the_planted_motion():
+    """Frontend(with_pose=True): match -> select -> RANSAC -> refit -> decomposition, nothing on
+    the host; the recovered rotation / translation direction match the synthetic camera motion
+    (yaw 0.02 rad, t = (0.05, 0, -1) per frame) and the host pipeline (oracle decomposition)."""
+    import torch
+    from b200slam.frontend import Frontend, FrontendConfig, sequence_batch
+    from b200slam.synthetic import tracking_sequence
+    from oracle import ransac_oracle as ro
+    F, N = 5, 1200
+    desc, kp = tracking_sequence(F, N, seed=3)
+    counts = np.full(F, N, np.int32)
+    fe = Frontend(FrontendConfig(hypotheses=512, max_matches=400, with_pose=True))
+    b = sequence_batch(torch.from_numpy(desc.reshape(-1, 32)).cuda(), torch.from_numpy(kp.reshape(-1, 2)).cuda(), counts, 0, F - 1, N)
+    res = fe.run(b)
+    torch.cuda.synchronize()
+    R, t = res.R.cpu().numpy().reshape(-1, 3, 3), res.t.cpu().numpy()
+    yaw = 0.02
+    Rt = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    tt = np.array([0.05, 0.0, -1.0]) / np.linalg.norm([0.05, 0.0, -1.0])
+    corr, cnt, mask = res.sel.corr.cpu().numpy(), res.sel.count.cpu().numpy(), res.inlier_mask.cpu().numpy()
+    for p in range(F - 1):
+        assert np.abs(R[p] - Rt).max() < 2e-2, p            # estimation noise (0.5 px, forward motion); exactness is checked against the oracle below
+        assert float(t[p] @ tt) > 0.99, p
+        sl = slice(p * 400, p * 400 + int(cnt[p]))
+        inl = mask[sl] > 0
+        Ro, to = ro.decompose_essential(res.E_refit[p].cpu().numpy().reshape(3, 3), corr[sl][inl][:, :2], corr[sl][inl][:, 2:], np.eye(3))
+        np.testing.assert_allclose(R[p], Ro, atol=1e-8)
+        np.testing.assert_allclose(t[p], to, atol=1e-8)
