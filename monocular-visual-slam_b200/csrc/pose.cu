@@ -365,49 +365,49 @@ __global__ void __launch_bounds__(kRefitThreads) refit_essential_kernel(
     if (lane < 9) eo[lane] = 0.0;
     return;
   }
-  // cyclic Jacobi on the 9x9 Gram matrix, warp-cooperative: lane k < 9 owns index k of the rotated rows / columns
+  // cyclic Jacobi on the 9x9 Gram matrix, warp-cooperative: lane k < 9 owns index k of the rotated rows /
+  // columns.  A rotation is skipped once |a_pq| <= eps sqrt(a_pp a_qq) (the criterion that gives a positive
+  // semi-definite matrix its small eigen-pairs to high relative accuracy); a sweep without rotations ends it.
+  __shared__ int s_rot;
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
-    if (lane < 9)
-      for (int j = 0; j < 9; ++j) off += (j != lane) ? fabs(s_M[lane][j]) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xFFFFFFFFu, off, o);
-    double diag = (lane < 9) ? fabs(s_M[lane][lane]) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xFFFFFFFFu, diag, o);
-    if (off <= 1e-22 * diag) break;
+    if (lane == 0) s_rot = 0;
+    __syncwarp();
     for (int p = 0; p < 8; ++p)
       for (int q = p + 1; q < 9; ++q) {
         if (lane == 0) {
-          const double apq = s_M[p][q];
+          const double apq = s_M[p][q], app = s_M[p][p], aqq = s_M[q][q];
           double c = 1.0, s = 0.0;
-          if (apq != 0.0) {
-            const double theta = (s_M[q][q] - s_M[p][p]) / (2.0 * apq);
+          if (fabs(apq) > 1.0e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+            const double theta = (aqq - app) / (2.0 * apq);
             const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
             c = rsqrt(fma(t, t, 1.0));
             s = t * c;
+            s_rot = 1;
           }
           s_cs[0] = c;
           s_cs[1] = s;
         }
         __syncwarp();
         const double c = s_cs[0], s = s_cs[1];
-        if (lane < 9) {  // M <- M J (columns p, q), V <- V J
-          const double mkp = s_M[lane][p], mkq = s_M[lane][q];
-          s_M[lane][p] = c * mkp - s * mkq;
-          s_M[lane][q] = s * mkp + c * mkq;
-          const double vkp = s_V[lane][p], vkq = s_V[lane][q];
-          s_V[lane][p] = c * vkp - s * vkq;
-          s_V[lane][q] = s * vkp + c * vkq;
-        }
-        __syncwarp();
-        if (lane < 9) {  // M <- J^T M (rows p, q)
-          const double mpk = s_M[p][lane], mqk = s_M[q][lane];
-          s_M[p][lane] = c * mpk - s * mqk;
-          s_M[q][lane] = s * mpk + c * mqk;
+        if (s != 0.0) {  // uniform across the warp
+          if (lane < 9) {  // M <- M J (columns p, q), V <- V J
+            const double mkp = s_M[lane][p], mkq = s_M[lane][q];
+            s_M[lane][p] = c * mkp - s * mkq;
+            s_M[lane][q] = s * mkp + c * mkq;
+            const double vkp = s_V[lane][p], vkq = s_V[lane][q];
+            s_V[lane][p] = c * vkp - s * vkq;
+            s_V[lane][q] = s * vkp + c * vkq;
+          }
+          __syncwarp();
+          if (lane < 9) {  // M <- J^T M (rows p, q)
+            const double mpk = s_M[p][lane], mqk = s_M[q][lane];
+            s_M[p][lane] = c * mpk - s * mqk;
+            s_M[q][lane] = s * mpk + c * mqk;
+          }
         }
         __syncwarp();
       }
+    if (s_rot == 0) break;
   }
   if (lane == 0) {
     int best = 0;
