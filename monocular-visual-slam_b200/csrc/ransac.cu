@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 //   |d - fl(d)|     <= 2 |num| delta + delta^2 + th^2 |den - fl(den)| + 4u (num^2 + th^2 den)
 // B below takes every constant 2x larger than that.
 constexpr int kScoreHThreads = 128;
-constexpr int kScoreHChunk = 1024;
+constexpr int kScoreHChunk = 256;   // 4 KB of shared memory: small enough to co-reside with the 220 KB K2s CTA of another stream
 
 __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
