@@ -69,51 +69,53 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
 // range (>= 0xFE00 after the row or the column is taken off again) otherwise.  Query tiles
 // carry an 18th, all-zero chunk so that the second half of the K = 32 index step multiplies
 // whatever follows the train tile's chunk 16 in shared memory by zero.
-__global__ void __launch_bounds__(256) expand_pm8_kernel(const uint8_t* __restrict__ desc,
+__global__ void __launch_bounds__(128) expand_pm8_kernel(const uint8_t* __restrict__ desc,
                                                          const int32_t* __restrict__ off,
                                                          const int32_t* __restrict__ src, int tiles_per_pair,
                                                          int train, int layout, uint4* __restrict__ out) {
+  // one CTA per (tile, pair), one thread per row: the row's 32 bytes are read once (2 x LDG.128)
+  // and its 17 / 18 k-chunks leave as STG.128 that are contiguous across the 128 threads.
   const int chunks = (layout == 1) ? kI8Chunks + 1 : kI8Chunks;
-  const int units = chunks * kI8Tile;
-  const int pair = blockIdx.y;
+  const int pair = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int o = off[pair];
   const int n = off[pair + 1] - o;
-  const int in0 = src ? src[pair] : o;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte unit within the pair's tiles
-  const int tile = u / units, w = u - tile * units;
-  if (tile >= tiles_per_pair) return;
   if (tile * kI8Tile >= n) return;  // tile never read
-  const int kc = w >> 7, r = w & 127;
+  const int in0 = src ? src[pair] : o;
   const int row = tile * kI8Tile + r;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (kc < 16) {
-    if (row < n) {
-      const uint32_t bits =
-          *reinterpret_cast<const uint16_t*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES + 2 * kc);
+  const bool valid = row < n;
+  uint4* dst = out + ((size_t)pair * tiles_per_pair + tile) * (size_t)(chunks * kI8Tile) + r;
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+  if (valid) {
+    const uint4* p = reinterpret_cast<const uint4*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES);
+    lo = __ldg(p);
+    hi = __ldg(p + 1);
+  }
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int kc = 0; kc < 16; ++kc) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      const uint32_t bits = (w[kc >> 1] >> (16 * (kc & 1))) & 0xFFFFu;   // descriptor bytes 2 kc, 2 kc + 1
       v.x = spread4(bits & 15u, train);
       v.y = spread4((bits >> 4) & 15u, train);
       v.z = spread4((bits >> 8) & 15u, train);
       v.w = spread4((bits >> 12) & 15u, train);
     }
-  } else if (kc == 16) {
-    if (layout == 0) {
-      if (row < n) {
-        v.x = (uint32_t)r | 0x40404000u;                 // [r, 64, 64, 64, 64, 0, ...]
-        v.y = 0x00000040u;
-      } else {
-        v.x = 0x7F7F7F7Fu;                               // [127 x9, 0, ...] -> acc = 65151
-        v.y = 0x7F7F7F7Fu;
-        v.z = 0x0000007Fu;
-      }
-    } else if (layout == 1) {
-      if (row < n) v = make_uint4(0x40404001u, 0x00000040u | ((uint32_t)r << 8), 0x40400000u, 0x00004040u);
-      else v = make_uint4(0x7F7F7F01u, 0x7F7F7F7Fu, 0x00007F7Fu, 0u);
-    } else {
-      if (row < n) v = make_uint4(0x40404000u | (uint32_t)r, 0x40400140u, 0x00004040u, 0u);
-      else v = make_uint4(0x7F7F7F7Fu, 0x0000017Fu, 0x7F7F0000u, 0x00007F7Fu);
-    }
-  }  // kc == 17 (layout 1): zeros
-  out[((size_t)pair * tiles_per_pair + tile) * units + w] = v;
+    dst[kc * kI8Tile] = v;
+  }
+  uint4 v;
+  if (layout == 0) {
+    v = valid ? make_uint4((uint32_t)r | 0x40404000u, 0x00000040u, 0u, 0u)     // [r, 64, 64, 64, 64, 0, ...]
+              : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x0000007Fu, 0u);         // [127 x9, 0, ...] -> acc = 65151
+  } else if (layout == 1) {
+    v = valid ? make_uint4(0x40404001u, 0x00000040u | ((uint32_t)r << 8), 0x40400000u, 0x00004040u)
+              : make_uint4(0x7F7F7F01u, 0x7F7F7F7Fu, 0x00007F7Fu, 0u);
+  } else {
+    v = valid ? make_uint4(0x40404000u | (uint32_t)r, 0x40400140u, 0x00004040u, 0u)
+              : make_uint4(0x7F7F7F7Fu, 0x0000017Fu, 0x7F7F0000u, 0x00007F7Fu);
+  }
+  dst[16 * kI8Tile] = v;
+  if (layout == 1) dst[17 * kI8Tile] = make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -1057,10 +1059,10 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   const int q_units = (single ? kI8Chunks + 1 : kI8Chunks) * kI8Tile;
   uint8_t* qx = static_cast<uint8_t*>(workspace);
   uint8_t* tx = qx + (size_t)n_pairs * qt * q_units * 16;
-  expand_pm8_kernel<<<dim3((qt * q_units + 255) / 256, n_pairs), 256, 0, st>>>(q, q_off, q_src, qt, 0, single ? 1 : 0,
+  expand_pm8_kernel<<<dim3(qt, n_pairs), 128, 0, st>>>(q, q_off, q_src, qt, 0, single ? 1 : 0,
                                                                                reinterpret_cast<uint4*>(qx));
   B2S_CUDA(cudaGetLastError());
-  expand_pm8_kernel<<<dim3((tt * kI8Units + 255) / 256, n_pairs), 256, 0, st>>>(t, t_off, t_src, tt, 1, single ? 2 : 0,
+  expand_pm8_kernel<<<dim3(tt, n_pairs), 128, 0, st>>>(t, t_off, t_src, tt, 1, single ? 2 : 0,
                                                                                 reinterpret_cast<uint4*>(tx));
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
