@@ -181,6 +181,17 @@ int b2s_refit_essential_batched(const float* corr, const int32_t* c_off, const i
                                 int n_pairs, const double* K_host, const double* Kinv_host, double* E_out, int32_t* n_used,
                                 void* stream);
 
+/* K8 — batched 5-point minimal solver (Nister): S samples per pair, up to 10 real essential
+ * matrices per sample.  corr must hold CALIBRATED (K^-1-normalised) points, as cv2.findEssentialMat
+ * normalises them before its solver (call sites slam_viewer.py:195, web_dashboard_server.py:145,
+ * visual_slam_offline_entry_point.py:51).  E_out = [pair][S][10][9] float64, unit Frobenius norm,
+ * unused slots zero (a zero E scores zero inliers, so E_out can go to the scoring entry points as
+ * H = 10 S hypotheses); n_sol [pair][S] (optional) = real solutions found; samples_in [pair][S][5]
+ * = host-drawn indices or NULL = device RNG. */
+int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, int S,
+                           const int32_t* samples_in, uint64_t seed, int32_t* samples_out, double* E_out, int32_t* n_sol,
+                           void* stream);
+
 /* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
  * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
  * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band

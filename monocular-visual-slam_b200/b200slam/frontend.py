@@ -282,6 +282,17 @@ class EssentialRansac:
         E = E[:n_pairs, :H]
         return (E, s_out[:n_pairs, :H]) if return_samples else E
 
+    def hypotheses_5pt(self, corr, c_off, c_count, n_pairs: int, S: int, *, samples=None, seed: int = 0, return_counts: bool = False):
+        """K8: 5-point minimal solver on CALIBRATED correspondences: S samples per pair, up to 10
+        real solutions each -> E [n_pairs, 10 S, 9] (unused slots zero), ready for score()."""
+        torch = _capi.require_cuda()
+        E = torch.empty((max(n_pairs, 1), max(S, 1), 10, 9), dtype=torch.float64, device=corr.device)
+        ns = torch.empty((max(n_pairs, 1), max(S, 1)), dtype=torch.int32, device=corr.device)
+        check(self._lib.b2s_five_point_batched(ptr(corr), ptr(c_off), ptr(c_count), n_pairs, S, ptr(samples),
+                                               C.c_uint64(seed & (2**64 - 1)), None, ptr(E), ptr(ns), current_stream()))
+        E = E[:n_pairs, :S].reshape(n_pairs, S * 10, 9)
+        return (E, ns[:n_pairs, :S]) if return_counts else E
+
     def score_tc(self, corr, c_off, c_count, n_pairs: int, E, th2: float, max_m: int, th2_per_pair=None, debug: bool = False):
         """K3t: the counts of score(precision=64) from the tensor cores (csrc/ransac_tc.cu).
         max_m >= every count.  debug=True also returns (num, den, band): the raw float32

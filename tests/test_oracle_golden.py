@@ -177,3 +177,16 @@ def test_homography_oracle_matches_reference(hgold):
         np.testing.assert_array_equal(inl, hgold[f"{name}/run_inliers"], err_msg=name)
         np.testing.assert_allclose(Hf, hgold[f"{name}/run_H"], rtol=1e-9, atol=1e-9, err_msg=name)
         np.testing.assert_array_equal(hom.draw_samples(np.random.default_rng(100 + int(np.flatnonzero(hgold["names"] == name)[0]) + 1), len(src), len(samples)), samples)
+
+
+def test_fivepoint_oracle_matches_cv2(golden_dir):
+    """The Nister-form restatement returns cv2.findEssentialMat's solution sets on exactly five points."""
+    from oracle import fivepoint_oracle as fp
+    g = np.load(golden_dir / "fivepoint_golden.npz")
+    total = hit = mine = 0
+    for k in range(int(g["n"])):
+        E = fp.five_point(g[f"c{k}/src"], g[f"c{k}/dst"])
+        total += len(g[f"c{k}/E"])
+        mine += len(E)
+        hit += fp.match_solution_sets(g[f"c{k}/E"], E, 1e-6)
+    assert total > 200 and hit >= total - 2 and mine <= total + 2, (total, hit, mine)
