@@ -203,6 +203,46 @@ def ransac_essential(src, dst, K, th: float = 0.01, max_iter: int = 2000, rng=No
     return eight_point_refit(src[inl], dst[inl], K), inl
 
 
+def find_essential_mat(points1, points2, K, threshold: float = 1.0, samples: int = 512, seed: int | None = None):
+    """Stand-in for the reference's ``cv2.findEssentialMat(pts1, pts2, K, method=cv2.RANSAC,
+    threshold=...)`` call sites (slam_viewer.py:195, web_dashboard_server.py:145,
+    visual_slam_offline_entry_point.py:51): 5-point RANSAC on the device (K8 minimal solver, the
+    float64 Sampson scoring of the 8-point path, the same winner rule).  Like OpenCV it calibrates
+    the points with ``K^-1`` and divides the pixel threshold by the mean focal length.  Returns
+    ``(E, mask)`` with E in calibrated coordinates (unit Frobenius norm; OpenCV scales differently)
+    and mask an (N, 1) uint8 column.  OpenCV's own sampling / termination are not reproduced
+    (third-party internals, parity unpinned)."""
+    import torch
+    from b200slam import _capi
+
+    _capi.require_cuda()
+    p1 = np.asarray(points1, np.float64).reshape(-1, 2)
+    p2 = np.asarray(points2, np.float64).reshape(-1, 2)
+    n = len(p1)
+    if n < 5:
+        return None, None
+    K = np.asarray(K, np.float64).reshape(3, 3)
+    Kinv = np.linalg.inv(K)
+    a = np.hstack([p1, np.ones((n, 1))]) @ Kinv.T
+    b = np.hstack([p2, np.ones((n, 1))]) @ Kinv.T
+    corr = np.hstack([a[:, :2] / a[:, 2:], b[:, :2] / b[:, 2:]]).astype(np.float32)
+    th = float(threshold) / (0.5 * (K[0, 0] + K[1, 1]))
+    R = _device_ransac()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    corr_d = torch.from_numpy(corr).to(dev)
+    off_d = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    cnt_d = torch.tensor([n], dtype=torch.int32, device=dev)
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
+    E = R.hypotheses_5pt(corr_d, off_d, cnt_d, 1, samples, seed=seed)
+    counts = R.score(corr_d, off_d, cnt_d, 1, E, th * th, precision=64)
+    best_h, _, mask = R.select(counts, corr_d, off_d, cnt_d, 1, E, th * th)
+    h = int(best_h[0])
+    if h < 0:
+        return None, None
+    return E[0, h].cpu().numpy().reshape(3, 3), mask.cpu().numpy().reshape(-1, 1).astype(np.uint8)
+
+
 def estimate_poses_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000):
     """``ransac_essential`` + ``decompose_essential`` (homography.py:302-345, 251-299) for many
     independent correspondence sets, everything on the device: ONE batched RANSAC (K4 + K3h +

@@ -68,3 +68,32 @@ def test_five_point_ransac_finds_the_motion():
     assert int(best_c[0]) > 0.6 * M
     inl = mask.cpu().numpy().astype(bool)
     assert inl[np.setdiff1d(np.arange(M), out)].mean() > 0.9 and inl[out].mean() < 0.1
+
+
+def test_find_essential_mat_agrees_with_cv2_on_inliers():
+    """pose_bridge.find_essential_mat (device 5-point RANSAC) against cv2.findEssentialMat on a
+    synthetic pixel-coordinate scene: same inlier set up to threshold-boundary points, same E up
+    to scale and sign on the calibrated points."""
+    import cv2
+    from integration.pose_bridge import find_essential_mat
+    rng = np.random.default_rng(19)
+    M = 300
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1.0]])
+    P = np.stack([rng.uniform(-8, 8, M), rng.uniform(-2, 2, M), rng.uniform(6, 40, M)], axis=1)
+    yaw = 0.04
+    Rt = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    P2 = P @ Rt.T + np.array([0.3, 0.0, -0.9])
+    px1 = (P / P[:, 2:]) @ K.T
+    px2 = (P2 / P2[:, 2:]) @ K.T
+    p1 = px1[:, :2]
+    p2 = px2[:, :2] + rng.normal(0, 0.3, (M, 2))
+    out = rng.permutation(M)[: M // 4]
+    p2[out] = np.stack([rng.uniform(0, 1241, len(out)), rng.uniform(0, 376, len(out))], axis=1)
+    E, mask = find_essential_mat(p1, p2, K, threshold=1.0, samples=512, seed=3)
+    Ec, mc = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.999, threshold=1.0)
+    assert E is not None and mask.shape == (M, 1)
+    agree = (mask.ravel() > 0) == (mc.ravel() > 0)
+    assert agree.mean() > 0.9          # both keep an unrefined minimal-sample E: points near the 1 px boundary differ
+    assert mask[out].mean() < 0.05 and mask[np.setdiff1d(np.arange(M), out)].mean() > 0.9
+    a, b = E / np.linalg.norm(E), Ec[:3] / np.linalg.norm(Ec[:3])
+    assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 0.05
