@@ -56,12 +56,15 @@ template <int WHICH>
 __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
   uint32_t x[8];
   double d[8];
-  float f[8];
+  float f[8], g[8];
+  unsigned long long p2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     x[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x;
     d[k] = 1.0 + 1e-9 * (double)x[k];
     f[k] = 1.0f + 1e-7f * (float)(x[k] & 1023);
+    g[k] = 1.0f - 1e-7f * (float)(x[k] & 511);
+    p2[k] = ((unsigned long long)__float_as_uint(f[k]) << 32) | __float_as_uint(f[k] * 0.5f);
   }
   const uint32_t c1 = blockIdx.x | 1u, c2 = threadIdx.x | 3u;
   for (int it = 0; it < iters; ++it) {
@@ -84,12 +87,22 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
         if (WHICH == 12)  // SEL with a loop-invariant predicate
           asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, 5;\n\tselp.b32 %0, %0, %1, p;\n\t}" : "+r"(x[k]) : "r"(c1), "r"(c2));
         if (WHICH == 13) asm volatile("prmt.b32 %0, %0, %1, 0x1032;" : "+r"(x[k]) : "r"(c1));
+        if (WHICH == 14) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]));  // FFMA2: counts as ONE instruction
+        if (WHICH == 15) {  // FFMA2 and scalar FFMA alternating (counted as ONE instruction per pair: compare the time with 14)
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(f[(k + 1) & 7]));
+        }
+        if (WHICH == 16) {  // one FFMA2 + two scalar FFMA
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(f[(k + 1) & 7]));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(g[k]) : "f"(g[(k + 1) & 7]));
+        }
       }
     }
   }
   uint32_t acc = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc ^= x[k] ^ (uint32_t)__double_as_longlong(d[k]) ^ __float_as_uint(f[k]);
+  for (int k = 0; k < 8; ++k) acc ^= x[k] ^ (uint32_t)__double_as_longlong(d[k]) ^ __float_as_uint(f[k]) ^ (uint32_t)p2[k] ^ (uint32_t)(p2[k] >> 32) ^ __float_as_uint(g[k]);
   if (acc == 0x12345678u) sink[0] = acc;  // keeps the chains alive, practically never taken
 }
 
@@ -174,7 +187,7 @@ int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink,
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(which >= 0 && which <= 13, "which must be 0..13");
+  B2S_REQUIRE(which >= 0 && which <= 16, "which must be 0..16");
   B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
   const int grid = sm_count() * ctas_per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -192,6 +205,9 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     case 11: pipe_kernel<11><<<grid, 256, 0, st>>>(iters, sink); break;
     case 12: pipe_kernel<12><<<grid, 256, 0, st>>>(iters, sink); break;
     case 13: pipe_kernel<13><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 14: pipe_kernel<14><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 15: pipe_kernel<15><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 16: pipe_kernel<16><<<grid, 256, 0, st>>>(iters, sink); break;
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }
   B2S_CUDA(cudaGetLastError());

@@ -132,30 +132,55 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   const float two_delta = 2.0f * delta;
   const float c0 = delta * delta + th2 * (8.0f * nE * (W1 * eta1 + W2 * eta2) + 4.0f * (eta1 * eta1 + eta2 * eta2));
   const float rho = 24.0f * kU;                                     // relative part, applied to num^2 + th^2 den
+  // The inner loop is branch-free: it counts the float32-certain inliers and records the
+  // undecidable evaluations of a group of 32 correspondences in a bit mask; the float64
+  // re-evaluation runs once per group over the set bits.  (Taking the detour inside the loop made
+  // every warp diverge on ~6 % of its steps — 32 lanes x 1.8e-3 on tracking data — and each detour
+  // is a ~25-deep dependent DFMA chain: 0.40 ms per bench step, against 0.30 ms this way.)
+  const float qnan = __int_as_float(0x7FC00000);
   int count = 0;
   for (int base = 0; base < M; base += kScoreHChunk) {
     const int n = min(kScoreHChunk, M - base);
+    const int n32 = (n + 31) & ~31;
     __syncthreads();
-    for (int m = threadIdx.x; m < n; m += kScoreHThreads) s_p[m] = __ldg(cp + base + m);
+    // the tail of the last group is padded with NaN: never a certain inlier, and its bits are masked off
+    for (int m = threadIdx.x; m < n32; m += kScoreHThreads)
+      s_p[m] = m < n ? __ldg(cp + base + m) : make_float4(qnan, qnan, qnan, qnan);
     __syncthreads();
-#pragma unroll 4
-    for (int m = 0; m < n; ++m) {
-      const float4 c = s_p[m];
-      const float a0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
-      const float a1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
-      const float a2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
-      const float b0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
-      const float b1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
-      const float num = fmaf(c.z, a0, fmaf(c.w, a1, a2));
-      const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
-      const float T = th2 * den;
-      const float q = num * num;
-      const float d = q - T;
-      const float B = fmaf(two_delta, fabsf(num), fmaf(rho, q + T, c0));
-      bool in = d < -B;
-      if (!(fabsf(d) > B))  // undecidable in float32 (or not finite): the float64 expression of K3 decides
-        in = sampson_inlier<double>(ed, (double)c.x, (double)c.y, (double)c.z, (double)c.w, th2d);
-      count += in ? 1 : 0;
+    for (int m0 = 0; m0 < n32; m0 += 32) {
+      uint32_t band = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 c = s_p[m0 + j];
+        const float a0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
+        const float a1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
+        const float a2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
+        const float b0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
+        const float b1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
+        const float num = fmaf(c.z, a0, fmaf(c.w, a1, a2));
+        const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+        const float T = th2 * den;
+        const float q = num * num;
+        const float d = q - T;
+        const float B = fmaf(two_delta, fabsf(num), fmaf(rho, q + T, c0));
+        // count += d < -B (certain inlier); band |= bit unless |d| > B (undecidable in float32, or not
+        // finite).  Two predicated instructions; the compiler's own form took 3.5 per step.
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.lt.f32 p, %2, %3;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t"
+            "setp.gt.f32 q, %4, %5;\n\t"
+            "@!q or.b32 %1, %1, %6;\n\t}"
+            : "+r"(count), "+r"(band)
+            : "f"(d), "f"(-B), "f"(fabsf(d)), "f"(B), "r"(1u << j));
+      }
+      const int left = n - m0;
+      if (left < 32) band &= (1u << left) - 1u;
+      while (band) {  // the float64 expression of K3 decides
+        const int j = __ffs((int)band) - 1;
+        band &= band - 1u;
+        const float4 c = s_p[m0 + j];
+        count += sampson_inlier<double>(ed, (double)c.x, (double)c.y, (double)c.z, (double)c.w, th2d) ? 1 : 0;
+      }
     }
   }
   if (live) counts[(size_t)pair * H + h] = count;
