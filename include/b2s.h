@@ -192,6 +192,23 @@ int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_
                            const int32_t* samples_in, uint64_t seed, int32_t* samples_out, double* E_out, int32_t* n_sol,
                            void* stream);
 
+/* K9 — bag-of-words candidate ranking, the step in front of the relocalizer's matching (next-row #4).
+ * b2s_bow_histogram_batched  replaces compute_bow_histogram (persistent_map.py:82-96) and
+ *                            BoWDatabase._compute_hist (loop_closure.py:36-48) for n_frames frames at
+ *                            once: desc = concatenated (N, 32) uint8 ORB descriptors read as 32 float
+ *                            values, f_off = CSR offsets (n_frames + 1), vocab = [k][32] float32
+ *                            centroids; nearest centroid by squared Euclidean distance in float64
+ *                            (sklearn pairwise_distances_argmin_min; first index on ties);
+ *                            words [total] (optional) = word of every descriptor, counts
+ *                            [n_frames][k] int32 (zeroed here), hist [n_frames][k] float32 =
+ *                            counts / n (float32 division, all zero for an empty frame).
+ * b2s_bow_cosine             replaces sklearn cosine_similarity([hist], hists)[0]
+ *                            (persistent_map.py:235, loop_closure.py:63): scores [n] float32, float64
+ *                            accumulation, zero rows score 0. */
+int b2s_bow_histogram_batched(const uint8_t* desc, const int32_t* f_off, int n_frames, int max_n, const float* vocab,
+                              int k, int32_t* words, int32_t* counts, float* hist, void* stream);
+int b2s_bow_cosine(const float* hist_q, const float* hists, int n, int k, float* scores, void* stream);
+
 /* K3t — the same counts as b2s_ransac_score_batched(precision 64 / 6464) from the tensor cores:
  * both bilinear forms of the Sampson test as tcgen05.mma kind::tf32 products of hi/lo-split
  * operands, float32 decision with a rigorous error bound, float64 re-evaluation inside the band

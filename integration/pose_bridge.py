@@ -519,6 +519,7 @@ def install() -> list[str]:
 
         relocalization_bridge.RelocalizationResult = persistent_map.RelocalizationResult
         bind("persistent_map", "MapRelocalizer", relocalization_bridge.BatchedMapRelocalizer)
+        bind("persistent_map", "compute_bow_histogram", relocalization_bridge.compute_bow_histogram)   # K9 (build_snapshot, :110-112)
     except Exception:
         pass
     return patched

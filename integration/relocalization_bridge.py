@@ -40,25 +40,81 @@ class RelocalizationResult:
     translation: np.ndarray
 
 
-def compute_bow_histogram(descriptors: np.ndarray, vocab: np.ndarray) -> np.ndarray:
-    """persistent_map.compute_bow_histogram (:82-96): nearest-centroid (L2, float32) word
-    counts, L1-normalised.  Host NumPy: BoW ranking is next-row #4, not the hot path."""
-    if descriptors is None or len(descriptors) == 0:
-        return np.zeros(vocab.shape[0], dtype=np.float32)
+def _validate_bow(descriptors, vocab):
+    """The argument checks of persistent_map.compute_bow_histogram (:85-90)."""
     if descriptors.ndim != 2:
         raise ValueError("Descriptors must be a 2D array")
     if vocab.ndim != 2:
         raise ValueError("Vocabulary must be a 2D array")
     if descriptors.shape[1] != vocab.shape[1]:
         raise ValueError("Descriptor dimensionality must match vocabulary")
-    desc = descriptors.astype(np.float32, copy=False)
-    voc = vocab.astype(np.float32, copy=False)
-    d2 = (desc * desc).sum(1)[:, None] - 2.0 * desc @ voc.T + (voc * voc).sum(1)[None]
+
+
+def _is_orb(descriptors, vocab) -> bool:
+    return descriptors.dtype == np.uint8 and descriptors.shape[1] == 32 and vocab.shape[1] == 32
+
+
+def host_bow_histogram(descriptors: np.ndarray, vocab: np.ndarray) -> np.ndarray:
+    """The reference's arithmetic on the host: what non-ORB descriptors (float32 / L2 maps, the
+    branch persistent_map._build_matcher keeps on OpenCV, :326-331) use, and what the CPU
+    control-flow tests inject.  Never a stand-in for the device path on ORB descriptors."""
+    if descriptors is None or len(descriptors) == 0:
+        return np.zeros(vocab.shape[0], dtype=np.float32)
+    _validate_bow(descriptors, vocab)
+    desc = descriptors.astype(np.float64)
+    voc = vocab.astype(np.float32, copy=False).astype(np.float64)
+    d2 = (voc * voc).sum(1)[None] - 2.0 * desc @ voc.T
     words = np.argmin(d2, axis=1)
     hist = np.bincount(words, minlength=vocab.shape[0]).astype(np.float32)
     if hist.sum() > 0:
         hist /= hist.sum()
     return hist
+
+
+def host_bow_scores(descriptors: np.ndarray, vocab: np.ndarray, hists: np.ndarray) -> np.ndarray:
+    """host_bow_histogram + sklearn's cosine_similarity, as persistent_map.py:234-235."""
+    return _cosine_row(host_bow_histogram(descriptors, vocab), hists)
+
+
+_BOW = {}
+
+
+def _bow_index(vocab: np.ndarray):
+    """One device copy of a vocabulary (keyed by its bytes)."""
+    from b200slam.frontend import BowIndex
+
+    v = np.ascontiguousarray(vocab, dtype=np.float32)
+    key = (v.shape, hash(v.tobytes()))
+    if key not in _BOW:
+        if len(_BOW) > 8:
+            _BOW.clear()
+        _BOW[key] = BowIndex(v)
+    return _BOW[key]
+
+
+def compute_bow_histogram(descriptors: np.ndarray, vocab: np.ndarray) -> np.ndarray:
+    """Drop-in for persistent_map.compute_bow_histogram (:82-96): nearest-centroid word counts,
+    L1-normalised, float32.  ORB descriptors ((N, 32) uint8) go through K9 on the device
+    (csrc/bow.cu); anything else keeps the reference's host arithmetic."""
+    if descriptors is None or len(descriptors) == 0:
+        return np.zeros(vocab.shape[0], dtype=np.float32)
+    _validate_bow(descriptors, vocab)
+    if not _is_orb(descriptors, vocab):
+        return host_bow_histogram(descriptors, vocab)
+    return _bow_index(vocab).histograms_host([descriptors])[0]
+
+
+def bow_histograms_batch(descriptor_blocks: Sequence[np.ndarray], vocab: np.ndarray) -> np.ndarray:
+    """The ``np.vstack([compute_bow_histogram(kf.descriptors, vocab) ...])`` of build_snapshot
+    (persistent_map.py:110-112) for a whole map in ONE launch -> float32 [n, k]."""
+    vocab = np.asarray(vocab)
+    blocks = [np.zeros((0, 32), np.uint8) if d is None or len(d) == 0 else np.asarray(d) for d in descriptor_blocks]
+    for d in blocks:
+        if len(d):
+            _validate_bow(d, vocab)
+    if not all(_is_orb(d, vocab) for d in blocks):
+        return np.vstack([host_bow_histogram(d, vocab) for d in blocks]) if blocks else np.zeros((0, vocab.shape[0]), np.float32)
+    return _bow_index(vocab).histograms_host(blocks)
 
 
 def _cosine_row(hist: np.ndarray, hists: np.ndarray) -> np.ndarray:
@@ -131,7 +187,7 @@ class BatchedMapRelocalizer:
 
     def __init__(self, snapshot, intrinsics: np.ndarray | None, *, min_matches: int = 60, min_inliers: int = 30,
                  max_candidates: int = 5, score_threshold: float = 0.75, ransac_threshold: float = 0.01,
-                 verify_geometry: bool = True, batch_matcher=None, pose_solver=None) -> None:
+                 verify_geometry: bool = True, batch_matcher=None, pose_solver=None, bow_scorer=None) -> None:
         if snapshot.bow_hists.size == 0:
             raise ValueError("Persistent map has no BoW histograms")
         if verify_geometry and intrinsics is None:
@@ -148,14 +204,15 @@ class BatchedMapRelocalizer:
         # injection points (tests run the control flow on the CPU with reference matchers)
         self._batch_matcher = batch_matcher or cross_check_batch
         self._pose_solver = pose_solver
+        self._bow_scorer = bow_scorer
         self._map_dev = None
+        self._bow_dev = None
 
     # ---- persistent_map.py:226-319 ----------------------------------------------------------
     def relocalize(self, keypoints, descriptors: np.ndarray):
         if descriptors is None or len(descriptors) == 0:
             raise ValueError("Descriptors are required for relocalization")
-        hist = compute_bow_histogram(descriptors, self.snapshot.bow_vocab)
-        scores = _cosine_row(hist, self.snapshot.bow_hists)
+        scores = self._bow_scores(descriptors)
         ranked = sorted(range(len(scores)), key=lambda idx: (-float(scores[idx]), int(self.snapshot.bow_frame_ids[idx])))
         cands = []
         for idx in ranked[: self.max_candidates]:
@@ -213,6 +270,26 @@ class BatchedMapRelocalizer:
         else:
             LOGGER.info("Relocalization failed: no candidates passed thresholds")
         return best
+
+    def _bow_scores(self, descriptors) -> np.ndarray:
+        """persistent_map.py:234-235: the query's BoW histogram and its cosine similarity to every
+        map histogram.  ORB descriptors: K9 on the device (vocabulary and map histograms resident,
+        one histogram launch + one cosine launch); other descriptors: the reference's host arithmetic."""
+        vocab, hists = self.snapshot.bow_vocab, self.snapshot.bow_hists
+        if self._bow_scorer is not None:
+            return np.asarray(self._bow_scorer(descriptors, vocab, hists))
+        descriptors = np.asarray(descriptors)
+        _validate_bow(descriptors, vocab)
+        if not _is_orb(descriptors, vocab):
+            return host_bow_scores(descriptors, vocab, hists)
+        if self._bow_dev is None:
+            self._bow_dev = _bow_index(vocab)
+            self._bow_dev.set_map(hists)
+        import torch
+        idx = self._bow_dev
+        d = torch.from_numpy(np.ascontiguousarray(descriptors)).to(idx.dev)
+        off = torch.tensor([0, len(descriptors)], dtype=torch.int32, device=idx.dev)
+        return idx.scores(idx.histograms(d, off, 1, len(descriptors))[0]).cpu().numpy()
 
     def _solve_poses(self, pairs):
         """estimate_pose_from_matches (homography.py:423-438) for every surviving candidate:

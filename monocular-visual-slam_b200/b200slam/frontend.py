@@ -423,6 +423,79 @@ class HomographyRansac:
         return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
 
 
+class BowIndex:
+    """K9 — bag-of-words candidate ranking on the device (csrc/bow.cu): the step in front of the
+    relocalizer's matching.  ``histograms`` = compute_bow_histogram (persistent_map.py:82-96) /
+    BoWDatabase._compute_hist (loop_closure.py:36-48) for a whole batch of frames in one launch;
+    ``scores`` = cosine_similarity([hist], hists)[0] (persistent_map.py:235, loop_closure.py:63)."""
+
+    def __init__(self, vocab: np.ndarray):
+        torch = _capi.require_cuda()
+        self.lib = _capi.load_library()
+        v = np.ascontiguousarray(vocab, dtype=np.float32)
+        if v.ndim != 2 or v.shape[0] == 0:
+            raise ValueError("BoW vocabulary must be a non-empty 2D array")
+        if v.shape[1] != DESC_BYTES:
+            raise ValueError(f"the device BoW path takes {DESC_BYTES}-dimensional (ORB) vocabularies")
+        self.k = int(v.shape[0])
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.vocab = torch.from_numpy(v).to(self.dev)
+        self.map_hists = None
+
+    def histograms(self, desc, f_off, n_frames: int, max_n: int, return_words: bool = False):
+        """desc: device uint8 [total, 32]; f_off: device int32 [n_frames + 1] -> hist float32 [n_frames, k]."""
+        import torch
+
+        hist = torch.empty((n_frames, self.k), dtype=torch.float32, device=self.dev)
+        counts = torch.empty((n_frames, self.k), dtype=torch.int32, device=self.dev)
+        words = torch.empty((int(desc.shape[0]),), dtype=torch.int32, device=self.dev) if return_words else None
+        check(self.lib.b2s_bow_histogram_batched(ptr(desc), ptr(f_off), n_frames, max_n, ptr(self.vocab), self.k,
+                                                 ptr(words), ptr(counts), ptr(hist), current_stream()))
+        return (hist, words) if return_words else hist
+
+    def histograms_host(self, desc_list: Sequence[np.ndarray], return_words: bool = False):
+        """Host lists of (N_i, 32) uint8 blocks -> NumPy [n, k] float32 (one upload, one launch)."""
+        import torch
+
+        blocks = [np.ascontiguousarray(d, dtype=np.uint8).reshape(-1, DESC_BYTES) if d is not None and len(d) else
+                  np.zeros((0, DESC_BYTES), np.uint8) for d in desc_list]
+        n = len(blocks)
+        if n == 0:
+            return np.zeros((0, self.k), np.float32)
+        off = np.zeros(n + 1, np.int32)
+        off[1:] = np.cumsum([len(b) for b in blocks])
+        allb = np.concatenate(blocks) if off[-1] else np.zeros((1, DESC_BYTES), np.uint8)
+        desc = torch.from_numpy(allb).to(self.dev)
+        out = self.histograms(desc, torch.from_numpy(off).to(self.dev), n, int(max(len(b) for b in blocks)), return_words)
+        if return_words:
+            return out[0].cpu().numpy(), out[1].cpu().numpy()[: off[-1]]
+        return out.cpu().numpy()
+
+    def set_map(self, hists):
+        """Keep the map's histograms [n, k] resident on the device."""
+        import torch
+
+        h = hists if hasattr(hists, "data_ptr") else torch.from_numpy(np.ascontiguousarray(hists, dtype=np.float32))
+        if h.ndim != 2 or h.shape[1] != self.k:
+            raise ValueError("map histograms must be [n, k]")
+        self.map_hists = h.to(self.dev, dtype=torch.float32).contiguous()
+
+    def scores(self, hist_q):
+        """hist_q: device float32 [k] (or host array) -> device float32 [n] cosine scores against the map."""
+        import torch
+
+        if self.map_hists is None:
+            raise ValueError("set_map() first")
+        q = hist_q if hasattr(hist_q, "data_ptr") else torch.from_numpy(np.ascontiguousarray(hist_q, dtype=np.float32))
+        q = q.to(self.dev, dtype=torch.float32).contiguous().reshape(-1)
+        if q.numel() != self.k:
+            raise ValueError("query histogram must have k entries")
+        n = int(self.map_hists.shape[0])
+        out = torch.empty((n,), dtype=torch.float32, device=self.dev)
+        check(self.lib.b2s_bow_cosine(ptr(q), ptr(self.map_hists), n, self.k, ptr(out), current_stream()))
+        return out
+
+
 @dataclass
 class FrontendConfig:
     """One pass of the hot path.  Defaults = configs/pipeline/kitti_default.json + the

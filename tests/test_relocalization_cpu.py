@@ -45,18 +45,18 @@ def _keyframes(pm, rng, n_kf, n_desc, dtype):
 
 
 def test_bow_histogram_and_ranking_match_reference(pm):
-    from integration.relocalization_bridge import BatchedMapRelocalizer, compute_bow_histogram
+    from integration.relocalization_bridge import BatchedMapRelocalizer, host_bow_histogram, host_bow_scores
     rng = np.random.default_rng(11)
     vocab = rng.normal(size=(24, 32)).astype(np.float32) * 60 + 128
     for dtype in (np.uint8, np.float32):
         kfs = _keyframes(pm, rng, 9, 80, dtype)
         snap = pm.build_snapshot(kfs, vocab)
         for kf in kfs:
-            np.testing.assert_allclose(compute_bow_histogram(kf.descriptors, vocab), pm.compute_bow_histogram(kf.descriptors, vocab))
+            np.testing.assert_allclose(host_bow_histogram(kf.descriptors, vocab), pm.compute_bow_histogram(kf.descriptors, vocab))
         for q in (kfs[4].descriptors, rng.integers(0, 256, (70, 32)).astype(dtype)):
             for thr in (0.0, 0.9, 0.999):
                 a = pm.MapRelocalizer(snap, None, verify_geometry=False, score_threshold=thr).relocalize(None, q)
-                b = BatchedMapRelocalizer(snap, None, verify_geometry=False, score_threshold=thr).relocalize(None, q)
+                b = BatchedMapRelocalizer(snap, None, verify_geometry=False, score_threshold=thr, bow_scorer=host_bow_scores).relocalize(None, q)
                 assert (a is None) == (b is None)
                 if a is not None:
                     assert (a.frame_id, a.match_count, a.inliers) == (b.frame_id, b.match_count, b.inliers)
@@ -64,12 +64,12 @@ def test_bow_histogram_and_ranking_match_reference(pm):
     with pytest.raises(ValueError):
         BatchedMapRelocalizer(snap, None, verify_geometry=True)
     with pytest.raises(ValueError):
-        BatchedMapRelocalizer(snap, None, verify_geometry=False).relocalize(None, np.zeros((0, 32), np.uint8))
+        BatchedMapRelocalizer(snap, None, verify_geometry=False, bow_scorer=host_bow_scores).relocalize(None, np.zeros((0, 32), np.uint8))
 
 
 def test_geometry_gates_and_best_rule_match_reference(pm, monkeypatch):
     import cv2
-    from integration.relocalization_bridge import BatchedMapRelocalizer
+    from integration.relocalization_bridge import BatchedMapRelocalizer, host_bow_scores
     rng = np.random.default_rng(5)
     vocab = rng.normal(size=(16, 32)).astype(np.float32) * 60 + 128
     kfs = _keyframes(pm, rng, 8, 120, np.uint8)
@@ -102,10 +102,10 @@ def test_geometry_gates_and_best_rule_match_reference(pm, monkeypatch):
                dict(min_matches=20, min_inliers=5, score_threshold=0.0, max_candidates=2),
                dict(min_matches=500, min_inliers=5, score_threshold=0.0, max_candidates=8)):
         a = pm.MapRelocalizer(snap, K, **kw).relocalize(kps, query)
-        b = BatchedMapRelocalizer(snap, K, batch_matcher=_cv2_batch, pose_solver=stub_solver, **kw).relocalize(kps, query)
+        b = BatchedMapRelocalizer(snap, K, batch_matcher=_cv2_batch, pose_solver=stub_solver, bow_scorer=host_bow_scores, **kw).relocalize(kps, query)
         assert (a is None) == (b is None), kw
         if a is not None:
             assert (a.frame_id, a.match_count, a.inliers) == (b.frame_id, b.match_count, b.inliers), kw
             assert abs(a.score - b.score) < 1e-9
     with pytest.raises(ValueError):
-        BatchedMapRelocalizer(snap, K, batch_matcher=_cv2_batch, pose_solver=stub_solver, score_threshold=0.0).relocalize(None, query)
+        BatchedMapRelocalizer(snap, K, batch_matcher=_cv2_batch, pose_solver=stub_solver, bow_scorer=host_bow_scores, score_threshold=0.0).relocalize(None, query)
