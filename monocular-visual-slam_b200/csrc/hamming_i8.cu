@@ -221,6 +221,21 @@ __device__ __forceinline__ uint32_t tc_mma_tile_pair(uint32_t d1, uint32_t d2, u
         "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
       : "r"(taddr))
 
+// 16 TMEM lanes x 128 accumulator columns -> 32 registers (tools/probes/ld16x256.cu): with gr = lane / 4,
+// tc = lane % 4, register j = 4 g + 2 r + b holds row  lane0 + gr + 8 r  and columns
+// 16 g + 4 tc + 2 b (low half) and + 1 (high half).  A thread owns whole 4-column groups of TWO rows.
+#define TMEM_LD_16X256_X8P(taddr, v)                                                                       \
+  asm volatile(                                                                                            \
+      "tcgen05.ld.sync.aligned.16x256b.x8.pack::16b.b32 "                                                  \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
+      : "r"(taddr))
+
 struct I8Params {
   const uint8_t* __restrict__ qx;  // expanded query tiles  [pair][q_tiles][34 KB]
   const uint8_t* __restrict__ tx;  // expanded train tiles  [pair][t_tiles][34 KB]
@@ -609,6 +624,7 @@ __device__ __forceinline__ void colmin_warp(uint32_t (&y)[64], int lane) {
   y[1] -= cfix + 0x00020002u;                                            // columns 4L+2 | 4L+3
 }
 
+template <int EPI, bool DBG>
 __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_q = smem;                                   // 2 x 36 KB: sub-tile a | sub-tile b of the item (18 chunks each)
@@ -741,6 +757,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
       }
     }
   } else {
+    if constexpr (EPI == 0) {
     // ===== epilogue: 4 sets of 4 warps; set s owns TMEM stage s, i.e. the tile pairs g with g%4 == s
     // (sub-tile s&1, every other train tile); warp%4 = TMEM lane quarter.  Four warps per scheduler
     // instead of two: the per-tile-pair work is a long dependent chain (TMEM load, folds, butterfly)
@@ -861,6 +878,174 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
     if (p.dbg && threadIdx.x == 64) {
       p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
       p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
+    }
+    } else {
+    // ===== epilogue, 16x256b form (default): same sets / stages / barriers as above, but the accumulator
+    // is read with tcgen05.ld.16x256b: a thread then owns 4 ROWS (gr, gr+8, gr+16, gr+24 of its warp's
+    // 32 TMEM lanes, gr = lane/4) x 32 columns (eight 4-column groups, 16 g + 4 (lane%4) ..+3) instead
+    // of 1 row x 128 columns.
+    //  * Column minimum: the four rows are folded inside the thread (2 instructions per register) and
+    //    only then cross lanes: 3 butterfly levels over 16 registers (14 exchanges) instead of 5 levels
+    //    over 64 (62 exchanges); it ends with lane L holding columns 4L..4L+3 exactly as before.
+    //  * Per-row top-2: 16 registers per row, two rows in lock step (independent dependency chains: with
+    //    64 of the 96 registers holding the accumulator ptxas otherwise runs one serial chain at a time
+    //    and the epilogue is latency-, not issue-bound); the results of two rows share a register
+    //    (row a | row b << 16), the four lanes that share a row merge in that packed form (4 SHFL per
+    //    level) and lane%4 = k finishes row k: one running top-2 per thread, as in the 32x32b form. =====
+    const int quarter = warp & 3;
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;
+    const uint32_t sub = set & 1u;
+    const int gr = lane >> 2, tc = lane & 3;
+    const int row = quarter * 32 + gr + 8 * tc;   // the tile-local row this lane keeps the running top-2 of
+    const uint32_t row_base = (uint32_t)(quarter * 32 + gr);
+    const uint32_t pick = tc == 0 ? 0x3210u : tc == 1 ? 0x1032u : tc == 2 ? 0x7654u : 0x5476u;  // row k = tc -> low half
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 128u;
+    uint32_t g_item = 0, hs = 0, n = 0;
+    long long w_tfull = 0;
+    const long long e_start = DBG ? clock64() : 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int pair = w / q_blocks, qb = w - pair * q_blocks;
+      const int nq = p.q_off[pair + 1] - p.q_off[pair];
+      const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
+      const int q0 = qb * 2 * kI8Tile + (int)sub * kI8Tile;
+      if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
+      const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+      const int rows_valid = max(0, min(kI8Tile, nq - q0));
+      uint32_t gbest = kNone, gsecond = kNone;
+      // this set's tile pairs: g = g_item + 2 t + sub with g % 4 == set, i.e. every other train tile
+      for (int t = (int)(((set >> 1) ^ (g_item >> 1)) & 1u); t < n_tt; t += 2) {
+        const uint32_t g = g_item + 2u * (uint32_t)t + sub;
+        const int tbase = t * kI8Tile;
+        const long long c0 = DBG ? clock64() : 0;
+        mbar_wait_bounded(&b_tfull[set], hs & 1u);
+        ++hs;
+        if (DBG) w_tfull += clock64() - c0;
+        tc_fence_after();
+        if (p.mode & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_go[(g + 4u) % kI8sGo]);
+          continue;
+        }
+        uint32_t ra[32], rb[32];
+        TMEM_LD_16X256_X8P(lane_addr, ra);
+        TMEM_LD_16X256_X8P(lane_addr + (16u << 16), rb);
+        tmem_ld_wait();
+        TMEM_REGS_READY(ra);
+        TMEM_REGS_READY(rb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_go[(g + 4u) % kI8sGo]);
+        // register i (0..15 = 2 g + b) of the first / second row held by a 32-register load
+#define B2S_R0(r, i) (r[4 * ((i) >> 1) + ((i) & 1)])
+#define B2S_R1(r, i) (r[4 * ((i) >> 1) + 2 + ((i) & 1)])
+        // ---- per-row top-2 of this tile: rows (0, 1) from ra, rows (2, 3) from rb, two rows in lock step ----
+        uint32_t pb[2], ps[2];  // packed results: row a in the low half, row b in the high half
+        if (!(p.mode & 8)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t(&r)[32] = h ? rb : ra;
+            // pass 1: minimum per 16-bit lane (even / odd columns of the 4-column groups)
+            uint32_t m0 = __vimin3_u16x2(B2S_R0(r, 0), B2S_R0(r, 1), B2S_R0(r, 2));
+            uint32_t m1 = __vimin3_u16x2(B2S_R1(r, 0), B2S_R1(r, 1), B2S_R1(r, 2));
+#pragma unroll
+            for (int i = 3; i < 15; i += 2) {
+              m0 = __vimin3_u16x2(m0, B2S_R0(r, i), B2S_R0(r, i + 1));
+              m1 = __vimin3_u16x2(m1, B2S_R1(r, i), B2S_R1(r, i + 1));
+            }
+            const uint32_t bb0 = __vminu2(m0, B2S_R0(r, 15)), bb1 = __vminu2(m1, B2S_R1(r, 15));
+            // pass 2: keys are unique within a row, so x + ~best wraps to 0xFFFF exactly for the minimum itself
+            const uint32_t cn0 = ~bb0, cn1 = ~bb1;
+            uint32_t a00 = kNone, a01 = kNone, a10 = kNone, a11 = kNone;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              a00 = __viaddmin_u16x2(B2S_R0(r, i), cn0, a00);
+              a10 = __viaddmin_u16x2(B2S_R1(r, i), cn1, a10);
+              a01 = __viaddmin_u16x2(B2S_R0(r, i + 1), cn0, a01);
+              a11 = __viaddmin_u16x2(B2S_R1(r, i + 1), cn1, a11);
+            }
+            const uint32_t ss0 = __vminu2(a00, a01) + bb0 + 0x00010001u;  // second per 16-bit lane (no carry: < 2^16 each)
+            const uint32_t ss1 = __vminu2(a10, a11) + bb1 + 0x00010001u;
+            // fold the even / odd halves of both rows at once: x = (row a even | row b even), y = (.. odd | .. odd)
+            const uint32_t x = __byte_perm(bb0, bb1, 0x5410), y = __byte_perm(bb0, bb1, 0x7632);
+            const uint32_t sx = __byte_perm(ss0, ss1, 0x5410), sy = __byte_perm(ss0, ss1, 0x7632);
+            pb[h] = __vminu2(x, y);
+            ps[h] = __vimin3_u16x2(__vmaxu2(x, y), sx, sy);
+          }
+          // the four lanes that share these rows hold disjoint columns: merge best / second, both row pairs
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, pb[h], o), os = __shfl_xor_sync(0xFFFFFFFFu, ps[h], o);
+              ps[h] = __vimin3_u16x2(__vmaxu2(pb[h], ob), ps[h], os);
+              pb[h] = __vminu2(pb[h], ob);
+            }
+          }
+          // lane%4 = k finishes row k; keys carry + row: take it off before widening
+          const uint32_t best16 = __byte_perm(pb[0], pb[1], pick) & 0xFFFFu, sec16 = __byte_perm(ps[0], ps[1], pick) & 0xFFFFu;
+          top2_insert(gbest, gsecond, key16_to_key32(best16 - (uint32_t)row, (uint32_t)tbase));
+          top2_insert(gbest, gsecond, key16_to_key32(sec16 - (uint32_t)row, (uint32_t)tbase));
+        }
+        // ---- column minima: the 4 rows inside the thread, then 3 butterfly levels over lane bits 2..4 ----
+        uint32_t y[64];   // colmin_step's signature; only y[0..15] are live
+        uint32_t cur[4] = {0u, 0u, 0u, 0u};
+        if (!(p.mode & 4)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __vminu2(__vimin3_u16x2(B2S_R0(ra, i), B2S_R1(ra, i), B2S_R0(rb, i)), B2S_R1(rb, i));
+          // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics):
+          // requested here, into the accumulator registers the fold just freed, and consumed after the
+          // butterfly (requesting them before the accumulator wait costs 4 registers through the top-2
+          // and measured slower: 892 vs 876 clk per tile pair)
+          {
+            const int nt_valid = min(kI8Tile, nt - tbase);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = 4 * lane + k;
+              cur[k] = (c < nt_valid) ? __ldcg(&p.bwd_best[to + tbase + c]) : 0u;
+            }
+          }
+          const uint32_t u16 = (lane >> 4) & 1, u8 = (lane >> 3) & 1, u4 = (lane >> 2) & 1;
+          colmin_step<16>(y, u16, 0u - u16, 16);
+          colmin_step<8>(y, u8, 0u - u8, 8);
+          colmin_step<4>(y, u4, 0u - u4, 4);
+          // register i of lane L is now position 2 (L/4) + i, i.e. columns 16 (L/4) + 4 (L%4) + 2 i, +1 = 4 L + 2 i, +1
+          const uint32_t cfix = (uint32_t)(4 * lane) * 0x10001u + 0x00010000u;
+          y[0] -= cfix;
+          y[1] -= cfix + 0x00020002u;
+        } else {
+          y[0] = y[1] = kNone;
+        }
+#undef B2S_R0
+#undef B2S_R1
+        const uint32_t cm16[4] = {y[0] & 0xFFFFu, y[0] >> 16, y[1] & 0xFFFFu, y[1] >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t key = key16_to_key32(cm16[k], (uint32_t)q0);
+          // rows_valid == 0: the whole sub-tile is padding and its MMAs read stale shared memory
+          if (rows_valid > 0 && cm16[k] < kKey16Valid && key < cur[k]) atomicMin(&p.bwd_best[to + tbase + 4 * lane + k], key);
+        }
+      }
+      g_item += 2u * (uint32_t)n_tt;
+      // the two sets of a sub-tile (even / odd train tiles) meet in shared memory; double buffered by
+      // item parity, so one named barrier per item is enough
+      uint2* mg = s_merge + (((n & 1u) * 2u + sub) << 7);
+      if (set >= 2u) mg[row] = make_uint2(gbest, gsecond);
+      asm volatile("bar.sync %0, 256;" ::"r"(1u + sub) : "memory");
+      if (set < 2u && row < rows_valid) {
+        const uint2 o = mg[row];
+        top2_insert(gbest, gsecond, o.x);
+        top2_insert(gbest, gsecond, o.y);
+        const int qo = p.q_off[pair];
+        p.fwd_best[qo + q0 + row] = gbest >= kKey32Pad ? kNone : gbest;
+        p.fwd_second[qo + q0 + row] = gsecond >= kKey32Pad ? kNone : gsecond;
+      }
+      ++n;
+    }
+    if (DBG && threadIdx.x == 64) {
+      p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
+      p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
+    }
     }
   }
 
@@ -1088,14 +1273,20 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   if (single) {
     static bool attr_set1 = false;
     if (!attr_set1) {
-      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kI8sSmemBytes));
+      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kI8sSmemBytes));
+      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kI8sSmemBytes));
       attr_set1 = true;
     }
     const long items = (long)((qt + 1) / 2) * n_pairs;
     const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
     if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
-    hamming_knn2_i8s_kernel<<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
+    if (p.mode & 16) hamming_knn2_i8s_kernel<0, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);   // 32x32b epilogue (A/B partner)
+    else if (p.dbg) hamming_knn2_i8s_kernel<1, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);   // with the stall counters
+    else hamming_knn2_i8s_kernel<1, false><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
     B2S_CUDA(cudaGetLastError());
     if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
     note_launch();

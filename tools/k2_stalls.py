@@ -37,7 +37,7 @@ for nd, var in ((128, 0), (256, 0), (128, 1), (128, 2), (128, 3), (128, 4)):
     per = (18 if var else 8)
     print(f"mma N={nd} variant {var}: {2*macs.value/ms/1e15:.2f} POP/s, {ms*1e-3*1.965e9/(2000*per):.1f} clk/instr")
 names = ["mma_total", "mma_wait_tempty", "mma_wait_full", "prod_wait_empty", "epi_total", "epi_wait_tfull"]
-for mode in ((0, 1, 4, 8, 12) if os.environ.get('K2S') else (0, 1, 2, 3)):
+for mode in ((0, 16, 1, 4, 8, 12, 20, 24) if os.environ.get('K2S') else (0, 1, 2, 3)):
     dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
     lib.b2s_hamming_i8_debug(C.c_void_p(dbg.data_ptr()), mode)
     m.knn2(batch)
@@ -47,5 +47,5 @@ for mode in ((0, 1, 4, 8, 12) if os.environ.get('K2S') else (0, 1, 2, 3)):
     lib.b2s_hamming_i8_debug(None, 0)
     d = dbg.cpu().numpy().reshape(148, 8).astype(np.float64)
     tp = d[:, 6]
-    print(f"mode {mode} (bit0: no epilogue work, bit1: no ring reloads): knn2 call {e0.elapsed_time(e1):.3f} ms; tile pairs/CTA {tp.mean():.0f}")
+    print(f"mode {mode} (bit0: no epilogue work, bit1: no ring reloads, bit2: no column minima, bit3: no top-2, bit4: 32x32b epilogue): knn2 call {e0.elapsed_time(e1):.3f} ms; tile pairs/CTA {tp.mean():.0f}")
     print("   " + "  ".join(f"{nm} {d[:, i].sum() / tp.sum():.0f}" for i, nm in enumerate(names)))
