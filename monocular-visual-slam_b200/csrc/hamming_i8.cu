@@ -636,6 +636,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
   uint64_t* b_qempty = bars + kI8sGo + kI8Stages + 4;    // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kI8sGo + kI8Stages + 6);
   uint2* s_merge = reinterpret_cast<uint2*>(s_tmem + 4);  // [2 item parities][2 sub-tiles][128]: the two sets of a sub-tile meet here
+  uint4* s_cur = reinterpret_cast<uint4*>(s_merge + 4 * kI8Tile);  // [16 epilogue warps][32 lanes]: staged bwd_best values (16x256b epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_blocks = (p.q_tiles + 1) >> 1;
@@ -911,11 +912,26 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
       if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
       const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
       const int rows_valid = max(0, min(kI8Tile, nq - q0));
+      const bool staged = (to & 3) == 0;
       uint32_t gbest = kNone, gsecond = kNone;
       // this set's tile pairs: g = g_item + 2 t + sub with g % 4 == set, i.e. every other train tile
       for (int t = (int)(((set >> 1) ^ (g_item >> 1)) & 1u); t < n_tt; t += 2) {
         const uint32_t g = g_item + 2u * (uint32_t)t + sub;
         const int tbase = t * kI8Tile;
+        // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics).
+        // Holding them in registers through the top-2 costs more than it saves (96 registers, 64 of them
+        // accumulator), and loading them late leaves the L2 latency exposed (10 % of the epilogue's
+        // samples sat on the first compare): cp.async parks them in this lane's shared-memory slot
+        // before the accumulator wait.  (.cg needs 16-byte alignment: a pair whose train offset is not
+        // a multiple of 4 rows takes the plain loads below.)
+        uint4* cur_slot = s_cur + (warp - 2) * 32 + lane;
+        if (staged) {
+          const int left = nt - tbase - 4 * lane;   // valid rows from this lane's first column on
+          const uint32_t nbytes = (uint32_t)(4 * max(0, min(4, left)));
+          const uint32_t* src = p.bwd_best + (left > 0 ? to + tbase + 4 * lane : to);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n\tcp.async.commit_group;"
+                       ::"r"(smem_u32(cur_slot)), "l"(src), "r"(nbytes) : "memory");
+        }
         const long long c0 = DBG ? clock64() : 0;
         mbar_wait_bounded(&b_tfull[set], hs & 1u);
         ++hs;
@@ -997,7 +1013,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           // requested here, into the accumulator registers the fold just freed, and consumed after the
           // butterfly (requesting them before the accumulator wait costs 4 registers through the top-2
           // and measured slower: 892 vs 876 clk per tile pair)
-          {
+          if (!staged) {
             const int nt_valid = min(kI8Tile, nt - tbase);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1015,6 +1031,11 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           y[1] -= cfix + 0x00020002u;
         } else {
           y[0] = y[1] = kNone;
+        }
+        if (staged) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          const uint4 c4 = *cur_slot;
+          cur[0] = c4.x; cur[1] = c4.y; cur[2] = c4.z; cur[3] = c4.w;
         }
 #undef B2S_R0
 #undef B2S_R1
@@ -1218,7 +1239,8 @@ constexpr size_t kI8SmemBytes =
     (size_t)(2 + kI8Stages) * kI8TileBytes + 2 * kI8ChunkBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
 constexpr size_t kI8sSmemBytes = 2 * (size_t)kI8sQTileBytes + (size_t)kI8Stages * kI8TileBytes + kI8ChunkBytes +
-                                 8 * (kI8sGo + kI8Stages + 6) + 16 + 4 * kI8Tile * sizeof(uint2);
+                                 8 * (kI8sGo + kI8Stages + 6) + 16 + 4 * kI8Tile * sizeof(uint2) +
+                                 16 * 32 * sizeof(uint4);  // + the epilogue warps' staging slots for the current column minima
 
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
