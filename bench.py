@@ -162,6 +162,7 @@ def b200_main(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = os.environ.get("B2S_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
@@ -399,6 +400,7 @@ def b200_main(a):
             "clocks": clk, "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": len(tracker.bounds), "cuda_graph": not a.no_graph, "steps_in_flight": depth,
                     "timing": "one CUDA-event pair around all K steps (steps overlap); inputs arrive over PCIe every step",
+                    "cpu_affinity_first_count": numa,
                     "ms_per_step": e2e_total / a.steps},
             "stage_ms": stages, "gpu_launches": warm_launches_per_step * a.steps, "gpu_launches_per_step": warm_launches_per_step,
             "hamming_variant": a.variant,
@@ -437,6 +439,20 @@ def sweep(lib, fe, batch, timed, a):
                 out[f"csa{csa}_r{rows}_w{warps}"] = float(np.mean(timed(lambda: fe.matcher.knn2(batch), 5, 2)))
     lib.b2s_hamming_set_config(*keep)
     return out
+
+
+def _bind_to_gpu_numa_node(local: int):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) BEFORE the pinned host
+    buffers are allocated, so that with several ranks on one box every rank's uploads come from its
+    own NUMA node instead of all of them crossing the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))[:1] + [len(os.sched_getaffinity(0))]
+    except Exception:
+        return None
 
 
 def main():

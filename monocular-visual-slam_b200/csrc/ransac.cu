@@ -252,7 +252,7 @@ constexpr int kEpThreads = 128;
 // AFFINE: the last row of Kinv is (0 0 1), so the dehomogenising divisions are by exactly 1.
 // KEYE: K = I, so the K^T F K product is the identity map.  Both are decided on the host.
 template <bool AFFINE, bool KEYE>
-__global__ void __launch_bounds__(kEpThreads) eight_point_kernel(
+__global__ void __launch_bounds__(kEpThreads, 4) eight_point_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count, int H,
     const int32_t* __restrict__ samples_in, uint64_t seed, int32_t* __restrict__ samples_out, const Mat3 K,
     const Mat3 Kinv, double* __restrict__ E_out) {
