@@ -7,8 +7,8 @@
 // the ratio + symmetry tests of match_orb_descriptors (/root/reference/homography.py:16-25)
 // and the keypoint gather of matches_to_points (feature_pipeline.py.bak:104-111).
 //
-// One CTA per pair.  Survivors become sort keys (distance<<22 | queryIdx) — unique, so a
-// plain bitonic sort in shared memory reproduces the reference's stable order exactly.
+// One CTA per pair; the stable order of the reference's sort is reproduced by a counting sort
+// (see the kernel).
 #include "common.cuh"
 
 namespace b2s {
@@ -37,65 +37,96 @@ struct SelectParams {
   int n_sort;  // power of two >= max_nq
 };
 
+// Distances are integers 0..256, so the reference's stable sort by distance is a COUNTING sort:
+// histogram of the survivors' distances, exclusive prefix sum, and a stable placement pass in which
+// one warp walks the query rows 32 at a time — __match_any_sync groups the lanes of equal distance,
+// the lowest lane of a group advances that distance's cursor, the others take the slots behind it in
+// lane (= query index) order.  2000 queries: 63 short iterations instead of the 66 block-wide
+// barrier passes of a 2048-key bitonic sort (37 -> ~10 us per 296 pairs).  sort_by_distance = 0 is the
+// same pass with a single bin (ascending query index).
+constexpr int kSelBins = 257;
+
 __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams p, const RatioLut lut) {
-  extern __shared__ uint32_t s_key[];
+  extern __shared__ uint16_t s_sel[];       // [n_sort] distance (0xFFFF = dropped) | [n_sort] query index by output position
+  __shared__ int s_hist[kSelBins + 31];
   __shared__ int s_count;
+  uint16_t* s_d = s_sel;
+  uint16_t* s_sorted = s_sel + p.n_sort;
   const int pair = blockIdx.x;
   const int qo = p.q_off[pair];
   const int nq = p.q_off[pair + 1] - qo;
   const int to = p.t_off[pair];
   const int ob = p.out_stride > 0 ? pair * p.out_stride : qo;  // output base
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-
-  // smallest power of two covering this pair (CTA-uniform)
-  int n = 32;
-  while (n < nq) n <<= 1;
-  if (n > p.n_sort) {  // caller's max_nq was too small for this pair: flag it, never overrun smem
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  if (nq > p.n_sort) {  // caller's max_nq was too small for this pair: flag it, never overrun smem
     if (tid == 0) p.out_count[pair] = -1;
     return;
   }
-
-  int mine = 0;
-  for (int i = tid; i < n; i += nthr) {
-    uint32_t key = kNone;
-    if (i < nq) {
-      const uint32_t b = p.fwd_best[qo + i];
-      bool keep = b < kInvalidRow;
-      const uint32_t d1 = b >> kIdxBits, j = b & kIdxMask;
-      if (keep && p.use_ratio) {
-        const uint32_t s2 = p.fwd_second[qo + i];
-        keep = (s2 < kInvalidRow) && (d1 < (uint32_t)lut.v[min(s2 >> kIdxBits, 256u)]);
-      }
-      if (keep && p.use_cross) keep = (p.bwd_best[to + j] & kIdxMask) == (uint32_t)i && p.bwd_best[to + j] < kInvalidRow;
-      if (keep) {
-        key = p.sort_by_distance ? ((d1 << kIdxBits) | (uint32_t)i) : (uint32_t)i;
-        ++mine;
-      }
-    }
-    s_key[i] = key;
-  }
-  if (mine) atomicAdd(&s_count, mine);
+  for (int b = tid; b < kSelBins + 31; b += nthr) s_hist[b] = 0;
   __syncthreads();
 
-  // bitonic sort, ascending; "none" keys sink to the end
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n; i += nthr) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint32_t a = s_key[i], b = s_key[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            s_key[i] = b;
-            s_key[ixj] = a;
-          }
+  // ---- survivors and the histogram of their distances ----
+  for (int i = tid; i < nq; i += nthr) {
+    const uint32_t b = p.fwd_best[qo + i];
+    bool keep = b < kInvalidRow;
+    const uint32_t d1 = b >> kIdxBits, j = b & kIdxMask;
+    if (keep && p.use_ratio) {
+      const uint32_t s2 = p.fwd_second[qo + i];
+      keep = (s2 < kInvalidRow) && (d1 < (uint32_t)lut.v[min(s2 >> kIdxBits, 256u)]);
+    }
+    if (keep && p.use_cross) {
+      const uint32_t bw = p.bwd_best[to + j];
+      keep = (bw & kIdxMask) == (uint32_t)i && bw < kInvalidRow;
+    }
+    const uint32_t bin = p.sort_by_distance ? min(d1, 256u) : 0u;
+    s_d[i] = keep ? (uint16_t)bin : (uint16_t)0xFFFFu;
+    if (keep) atomicAdd(&s_hist[bin], 1);
+  }
+  __syncthreads();
+
+  if (tid < 32) {
+    // ---- exclusive prefix sum over the 257 bins (9 per lane) ----
+    int local[9], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      local[k] = s_hist[lane * 9 + k];   // bins >= 257 are zero padding
+      sum += local[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      s_hist[lane * 9 + k] = run;        // now: next free output position of this distance
+      run += local[k];
+    }
+    if (lane == 31) s_count = incl;
+    __syncwarp();
+    // ---- stable placement: ascending query index within a distance ----
+    for (int base = 0; base < nq; base += 32) {
+      const int i = base + lane;
+      const uint32_t dd = i < nq ? (uint32_t)s_d[i] : 0xFFFFu;
+      const bool keep = dd != 0xFFFFu;
+      const uint32_t active = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) {
+        const uint32_t grp = __match_any_sync(active, dd);
+        const int leader = __ffs((int)grp) - 1;
+        int pos = 0;
+        if (lane == leader) {
+          pos = s_hist[dd];
+          s_hist[dd] = pos + __popc(grp);
         }
+        pos = __shfl_sync(grp, pos, leader);
+        s_sorted[pos + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)i;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
+  __syncthreads();
 
   int count = s_count;
   if (p.max_matches > 0 && count > p.max_matches) count = p.max_matches;
@@ -106,7 +137,7 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
   if (tid == 0) p.out_count[pair] = count;
   const int kq0 = p.q_src ? p.q_src[pair] : qo, kt0 = p.t_src ? p.t_src[pair] : to;
   for (int k = tid; k < count; k += nthr) {
-    const uint32_t i = s_key[k] & kIdxMask;
+    const uint32_t i = s_sorted[k];
     const uint32_t b = p.fwd_best[qo + i];
     const uint32_t j = b & kIdxMask;
     p.out_q[ob + k] = (int32_t)i;
@@ -165,9 +196,9 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
   p.max_matches = max_matches;
   int n = 32;
   while (n < max_nq) n <<= 1;
-  p.n_sort = n;
-  const size_t smem = sizeof(uint32_t) * (size_t)n;
-  const int threads = n >= 2048 ? 1024 : (n / 2 < 32 ? 32 : n / 2);
+  p.n_sort = n;   // capacity of the shared-memory arrays (rows per pair)
+  const size_t smem = 2 * sizeof(uint16_t) * (size_t)n;
+  const int threads = n >= 1024 ? 1024 : (n < 64 ? 64 : n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (smem > 48 * 1024) {
     B2S_CUDA(cudaFuncSetAttribute(select_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
