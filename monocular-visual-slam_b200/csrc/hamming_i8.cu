@@ -59,6 +59,15 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
   return train ? (0xF8F8F8F8u - sp * 0xF0u) : (0x08080808u + sp * 0xF0u);
 }
 
+// layout 3 (shipped, 16x256b epilogue): UNIFIED tiles, 18 chunks, the same tile serves a frame as query
+// and as train operand.  Data: bit clear / set -> +8 / -8 on both sides, so the 8 data K-steps give
+// 64 (256 - 2 ham) = 2^14 - 128 ham: the accumulator DEcreases with the distance.  The index K-step
+// multiplies the query tile's chunk 16 with the train tile's chunk 17:
+//     A (chunk 16) [-1, r, 127, 127, 127, 127, 2, 0..]     B (chunk 17) [c, -1, 127, 127, 127, 6, 1, 0..]
+// = -c - r + 3 * 16129 + 762 + 2 = 49151 - c - r, so that  acc = 65535 - (128 ham + c + r) = ~key:
+// the COMPLEMENT of the 16-bit key of layouts 1 / 2.  The epilogue takes maxima instead of minima
+// and complements its few results.  Padding rows are all zero on both sides: acc = 0, below every
+// real value (>= 32513), and 65535 = "none" after the complement.
 // layout 0: two-product tiles (17 chunks; index chunk [r, 64 x4, 0..], padding rows [127 x9, 0..]).
 // layout 1 / 2: single-product query / train tiles.  There the index K-step multiplies the
 // QUERY tile's own chunk 16 (A side) with the TRAIN tile's chunk 16 (B side), 14 int8 slots:
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(128) expand_pm8_kernel(const uint8_t* __restri
                                                          int train, int layout, uint4* __restrict__ out) {
   // one CTA per (tile, pair), one thread per row: the row's 32 bytes are read once (2 x LDG.128)
   // and its 17 / 18 k-chunks leave as STG.128 that are contiguous across the 128 threads.
-  const int chunks = (layout == 1) ? kI8Chunks + 1 : kI8Chunks;
+  const int chunks = (layout == 1 || layout == 3) ? kI8Chunks + 1 : kI8Chunks;
   const int pair = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int o = off[pair];
   const int n = off[pair + 1] - o;
@@ -96,14 +105,23 @@ __global__ void __launch_bounds__(128) expand_pm8_kernel(const uint8_t* __restri
     uint4 v = make_uint4(0, 0, 0, 0);
     if (valid) {
       const uint32_t bits = (w[kc >> 1] >> (16 * (kc & 1))) & 0xFFFFu;   // descriptor bytes 2 kc, 2 kc + 1
-      v.x = spread4(bits & 15u, train);
-      v.y = spread4((bits >> 4) & 15u, train);
-      v.z = spread4((bits >> 8) & 15u, train);
-      v.w = spread4((bits >> 12) & 15u, train);
+      const bool tr = train && layout != 3;   // unified tiles: one sign for both roles
+      v.x = spread4(bits & 15u, tr);
+      v.y = spread4((bits >> 4) & 15u, tr);
+      v.z = spread4((bits >> 8) & 15u, tr);
+      v.w = spread4((bits >> 12) & 15u, tr);
     }
     dst[kc * kI8Tile] = v;
   }
   uint4 v;
+  if (layout == 3) {
+    // unified tile: chunk 16 = index chunk of the row as a QUERY row (A side), chunk 17 = as a TRAIN row
+    // (B side); padding rows are all zero.  See the 16x256b epilogue for the arithmetic.
+    const uint32_t rr = (uint32_t)r;
+    dst[16 * kI8Tile] = valid ? make_uint4(0x7F7F00FFu | (rr << 8), 0x00027F7Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    dst[17 * kI8Tile] = valid ? make_uint4(0x7F7FFF00u | rr, 0x0001067Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   if (layout == 0) {
     v = valid ? make_uint4((uint32_t)r | 0x40404000u, 0x00000040u, 0u, 0u)     // [r, 64, 64, 64, 64, 0, ...]
               : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x0000007Fu, 0u);         // [127 x9, 0, ...] -> acc = 65151
@@ -586,7 +604,7 @@ __device__ __forceinline__ uint32_t tc_mma_tile_single(uint32_t d, uint64_t qdes
 // the FMA pipe; the epilogue is bound by whichever of the two pipes carries more, so the
 // selection goes to the FMA pipe (3 instructions) and only the minimum stays on the ALU pipe.
 //   e = a - b;  send = up*e + b  (= up ? a : b);  keep = (-up)*e + a  (= up ? b : a)   (exact mod 2^32)
-template <int N>
+template <int N, bool MAX = false>
 __device__ __forceinline__ void colmin_step(uint32_t (&y)[64], uint32_t up, uint32_t nup, int lane_mask) {
 #pragma unroll
   for (int i = 0; i < N / 2; ++i) {
@@ -602,7 +620,8 @@ __device__ __forceinline__ void colmin_step(uint32_t (&y)[64], uint32_t up, uint
           : "=r"(send), "=r"(keep)
           : "r"(y[i]), "r"(y[i + N / 2]), "r"(up), "r"(nup));
     }
-    y[i] = __vminu2(keep, __shfl_xor_sync(0xFFFFFFFFu, send, lane_mask));
+    const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, send, lane_mask);
+    y[i] = MAX ? __vmaxu2(keep, got) : __vminu2(keep, got);
   }
 }
 
@@ -644,8 +663,13 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
 
   // the index K-step reads one chunk past the last ring slot (times the query tile's zero chunk):
   // keep that chunk inside the allocation and defined
-  for (int i = threadIdx.x; i < kI8Tile; i += kI8sThreads)
+  for (int i = threadIdx.x; i < kI8Tile; i += kI8sThreads) {
     reinterpret_cast<uint4*>(s_t + kI8Stages * kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (EPI == 1) {  // unified tiles: the query slots' chunk 17 is never loaded and must read as zero
+      reinterpret_cast<uint4*>(s_q + kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(s_q + kI8sQTileBytes + kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   if (threadIdx.x == 0) {
@@ -682,7 +706,11 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         if (q0 >= nq || nt == 0) continue;
         const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
         const bool has_b = q0 + kI8Tile < nq;
-        const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kI8TileBytes;
+        // EPI 1: unified 18-chunk tiles on both sides; a query slot takes chunks 0..16 (data + its A-side
+        // index chunk), a train slot chunks 0..15 and chunk 17 (its B-side index chunk)
+        constexpr uint32_t kTStride = EPI == 1 ? (uint32_t)kI8sQTileBytes : (uint32_t)kI8TileBytes;
+        constexpr uint32_t kQBytes = EPI == 1 ? (uint32_t)kI8TileBytes : (uint32_t)kI8sQTileBytes;
+        const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kTStride;
         const uint8_t* qsrc = p.qx + ((size_t)pair * p.q_tiles + 2 * qb) * kI8sQTileBytes;
         for (int t = 0; t < n_tt; ++t, ++tau) {
           const uint32_t s = tau % kI8Stages, g = 2u * tau;
@@ -694,18 +722,26 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           const bool skip_t = (p.mode & 2) && tau >= kI8Stages;
           if (t == 0) {
             if (n >= 1) mbar_wait_bounded(&b_qempty[0], (n - 1u) & 1u);
-            mbar_arrive_expect_tx(go_a, kI8sQTileBytes + (skip_t ? 0 : kI8TileBytes));
-            bulk_g2s(s_q, qsrc, kI8sQTileBytes, go_a);
+            mbar_arrive_expect_tx(go_a, kQBytes + (skip_t ? 0 : kI8TileBytes));
+            bulk_g2s(s_q, qsrc, kQBytes, go_a);
           } else if (skip_t) {
             mbar_arrive(go_a);
           } else {
             mbar_arrive_expect_tx(go_a, kI8TileBytes);
           }
-          if (!skip_t) bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, go_a);
+          if (!skip_t) {
+            if (EPI == 1) {
+              bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kTStride, 16 * kI8ChunkBytes, go_a);
+              bulk_g2s(s_t + (size_t)s * kI8TileBytes + 16 * kI8ChunkBytes, tsrc + (size_t)t * kTStride + 17 * kI8ChunkBytes,
+                       kI8ChunkBytes, go_a);
+            } else {
+              bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, go_a);
+            }
+          }
           if (t == 0 && has_b) {
             if (n >= 1) mbar_wait_bounded(&b_qempty[1], (n - 1u) & 1u);
-            mbar_arrive_expect_tx(go_b, kI8sQTileBytes);
-            bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kI8sQTileBytes, go_b);
+            mbar_arrive_expect_tx(go_b, kQBytes);
+            bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kQBytes, go_b);
           } else {
             mbar_arrive(go_b);
           }
@@ -962,31 +998,32 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           for (int h = 0; h < 2; ++h) {
             const uint32_t(&r)[32] = h ? rb : ra;
             // pass 1: minimum per 16-bit lane (even / odd columns of the 4-column groups)
-            uint32_t m0 = __vimin3_u16x2(B2S_R0(r, 0), B2S_R0(r, 1), B2S_R0(r, 2));
-            uint32_t m1 = __vimin3_u16x2(B2S_R1(r, 0), B2S_R1(r, 1), B2S_R1(r, 2));
+            uint32_t m0 = __vimax3_u16x2(B2S_R0(r, 0), B2S_R0(r, 1), B2S_R0(r, 2));
+            uint32_t m1 = __vimax3_u16x2(B2S_R1(r, 0), B2S_R1(r, 1), B2S_R1(r, 2));
 #pragma unroll
             for (int i = 3; i < 15; i += 2) {
-              m0 = __vimin3_u16x2(m0, B2S_R0(r, i), B2S_R0(r, i + 1));
-              m1 = __vimin3_u16x2(m1, B2S_R1(r, i), B2S_R1(r, i + 1));
+              m0 = __vimax3_u16x2(m0, B2S_R0(r, i), B2S_R0(r, i + 1));
+              m1 = __vimax3_u16x2(m1, B2S_R1(r, i), B2S_R1(r, i + 1));
             }
-            const uint32_t bb0 = __vminu2(m0, B2S_R0(r, 15)), bb1 = __vminu2(m1, B2S_R1(r, 15));
-            // pass 2: keys are unique within a row, so x + ~best wraps to 0xFFFF exactly for the minimum itself
-            const uint32_t cn0 = ~bb0, cn1 = ~bb1;
-            uint32_t a00 = kNone, a01 = kNone, a10 = kNone, a11 = kNone;
+            const uint32_t bb0 = __vmaxu2(m0, B2S_R0(r, 15)), bb1 = __vmaxu2(m1, B2S_R1(r, 15));
+            // pass 2: values are unique within a row (or zero padding, never the largest of a real row), so
+            // x - best wraps to 0 exactly for the maximum itself and keeps the order of everything below it
+            const uint32_t cn0 = __vneg2(bb0), cn1 = __vneg2(bb1);
+            uint32_t a00 = 0u, a01 = 0u, a10 = 0u, a11 = 0u;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-              a00 = __viaddmin_u16x2(B2S_R0(r, i), cn0, a00);
-              a10 = __viaddmin_u16x2(B2S_R1(r, i), cn1, a10);
-              a01 = __viaddmin_u16x2(B2S_R0(r, i + 1), cn0, a01);
-              a11 = __viaddmin_u16x2(B2S_R1(r, i + 1), cn1, a11);
+              a00 = __viaddmax_u16x2(B2S_R0(r, i), cn0, a00);
+              a10 = __viaddmax_u16x2(B2S_R1(r, i), cn1, a10);
+              a01 = __viaddmax_u16x2(B2S_R0(r, i + 1), cn0, a01);
+              a11 = __viaddmax_u16x2(B2S_R1(r, i + 1), cn1, a11);
             }
-            const uint32_t ss0 = __vminu2(a00, a01) + bb0 + 0x00010001u;  // second per 16-bit lane (no carry: < 2^16 each)
-            const uint32_t ss1 = __vminu2(a10, a11) + bb1 + 0x00010001u;
+            const uint32_t ss0 = __vadd2(__vmaxu2(a00, a01), bb0);  // second largest per 16-bit lane (mod 2^16 per lane)
+            const uint32_t ss1 = __vadd2(__vmaxu2(a10, a11), bb1);
             // fold the even / odd halves of both rows at once: x = (row a even | row b even), y = (.. odd | .. odd)
             const uint32_t x = __byte_perm(bb0, bb1, 0x5410), y = __byte_perm(bb0, bb1, 0x7632);
             const uint32_t sx = __byte_perm(ss0, ss1, 0x5410), sy = __byte_perm(ss0, ss1, 0x7632);
-            pb[h] = __vminu2(x, y);
-            ps[h] = __vimin3_u16x2(__vmaxu2(x, y), sx, sy);
+            pb[h] = __vmaxu2(x, y);
+            ps[h] = __vimax3_u16x2(__vminu2(x, y), sx, sy);
           }
           // the four lanes that share these rows hold disjoint columns: merge best / second, both row pairs
 #pragma unroll
@@ -994,12 +1031,12 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, pb[h], o), os = __shfl_xor_sync(0xFFFFFFFFu, ps[h], o);
-              ps[h] = __vimin3_u16x2(__vmaxu2(pb[h], ob), ps[h], os);
-              pb[h] = __vminu2(pb[h], ob);
+              ps[h] = __vimax3_u16x2(__vminu2(pb[h], ob), ps[h], os);
+              pb[h] = __vmaxu2(pb[h], ob);
             }
           }
-          // lane%4 = k finishes row k; keys carry + row: take it off before widening
-          const uint32_t best16 = __byte_perm(pb[0], pb[1], pick) & 0xFFFFu, sec16 = __byte_perm(ps[0], ps[1], pick) & 0xFFFFu;
+          // lane%4 = k finishes row k: complement (acc = ~key), then the keys carry + row: take it off before widening
+          const uint32_t best16 = ~__byte_perm(pb[0], pb[1], pick) & 0xFFFFu, sec16 = ~__byte_perm(ps[0], ps[1], pick) & 0xFFFFu;
           top2_insert(gbest, gsecond, key16_to_key32(best16 - (uint32_t)row, (uint32_t)tbase));
           top2_insert(gbest, gsecond, key16_to_key32(sec16 - (uint32_t)row, (uint32_t)tbase));
         }
@@ -1008,7 +1045,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         uint32_t cur[4] = {0u, 0u, 0u, 0u};
         if (!(p.mode & 4)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __vminu2(__vimin3_u16x2(B2S_R0(ra, i), B2S_R1(ra, i), B2S_R0(rb, i)), B2S_R1(rb, i));
+          for (int i = 0; i < 16; ++i) y[i] = __vmaxu2(__vimax3_u16x2(B2S_R0(ra, i), B2S_R1(ra, i), B2S_R0(rb, i)), B2S_R1(rb, i));
           // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics):
           // requested here, into the accumulator registers the fold just freed, and consumed after the
           // butterfly (requesting them before the accumulator wait costs 4 registers through the top-2
@@ -1022,13 +1059,15 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
             }
           }
           const uint32_t u16 = (lane >> 4) & 1, u8 = (lane >> 3) & 1, u4 = (lane >> 2) & 1;
-          colmin_step<16>(y, u16, 0u - u16, 16);
-          colmin_step<8>(y, u8, 0u - u8, 8);
-          colmin_step<4>(y, u4, 0u - u4, 4);
+          colmin_step<16, true>(y, u16, 0u - u16, 16);
+          colmin_step<8, true>(y, u8, 0u - u8, 8);
+          colmin_step<4, true>(y, u4, 0u - u4, 4);
           // register i of lane L is now position 2 (L/4) + i, i.e. columns 16 (L/4) + 4 (L%4) + 2 i, +1 = 4 L + 2 i, +1
+          // acc = 65535 - (128 ham + column + row): complement and take the column off in one subtraction
+          // (no borrow between the halves: 65535 - column >= acc)
           const uint32_t cfix = (uint32_t)(4 * lane) * 0x10001u + 0x00010000u;
-          y[0] -= cfix;
-          y[1] -= cfix + 0x00020002u;
+          y[0] = (0xFFFFFFFFu - cfix) - y[0];
+          y[1] = (0xFFFFFFFFu - cfix - 0x00020002u) - y[1];
         } else {
           y[0] = y[1] = kNone;
         }
@@ -1244,7 +1283,7 @@ constexpr size_t kI8sSmemBytes = 2 * (size_t)kI8sQTileBytes + (size_t)kI8Stages 
 
 size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
-  return (size_t)n_pairs * (qt * kI8sQTileBytes + tt * kI8TileBytes);  // sized for the larger (single-product) layout
+  return (size_t)n_pairs * (qt + tt) * kI8sQTileBytes;  // sized for the largest layout (unified 18-chunk tiles on both sides)
 }
 
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
@@ -1263,13 +1302,14 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "i8 variant needs %zu workspace bytes (b2s_hamming_workspace_bytes_v), got %zu", need, workspace_bytes);
   B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
+  const bool unified = single && !(g_i8_mode & 16);   // the 16x256b epilogue reads unified tiles (layout 3)
   const int q_units = (single ? kI8Chunks + 1 : kI8Chunks) * kI8Tile;
   uint8_t* qx = static_cast<uint8_t*>(workspace);
   uint8_t* tx = qx + (size_t)n_pairs * qt * q_units * 16;
-  expand_pm8_kernel<<<dim3(qt, n_pairs), 128, 0, st>>>(q, q_off, q_src, qt, 0, single ? 1 : 0,
+  expand_pm8_kernel<<<dim3(qt, n_pairs), 128, 0, st>>>(q, q_off, q_src, qt, 0, unified ? 3 : single ? 1 : 0,
                                                                                reinterpret_cast<uint4*>(qx));
   B2S_CUDA(cudaGetLastError());
-  expand_pm8_kernel<<<dim3(tt, n_pairs), 128, 0, st>>>(t, t_off, t_src, tt, 1, single ? 2 : 0,
+  expand_pm8_kernel<<<dim3(tt, n_pairs), 128, 0, st>>>(t, t_off, t_src, tt, 1, unified ? 3 : single ? 2 : 0,
                                                                                 reinterpret_cast<uint4*>(tx));
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
