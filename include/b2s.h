@@ -192,6 +192,23 @@ int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_
                            const int32_t* samples_in, uint64_t seed, int32_t* samples_out, double* E_out, int32_t* n_sol,
                            void* stream);
 
+/* b2s_hamming_knn2_batched (variant B2S_VARIANT_I8MMA1) for batches whose pairs SHARE descriptor blocks:
+ * consecutive-frame tracking (frame k+1 is the train side of pair k and the query side of pair k+1,
+ * slam_api.py:352-353) and relocalization (one query frame against every keyframe,
+ * persistent_map.py:244-309).  Every distinct block is expanded to tensor-core operand tiles ONCE.
+ * desc = the one descriptor buffer; block b = blk_rows[b] rows starting at row blk_row0[b], its
+ * tiles start at tile blk_tile0[b] (prefix sum of ceil(rows / 128); total_tiles in all);
+ * q_xtile[p] / t_xtile[p] = first tile of pair p's query / train block; q_off / t_off = CSR of the
+ * OUTPUT rows (q_off[p+1] - q_off[p] must equal the query block's rows).  All index arrays int32 on
+ * the device.  Outputs as b2s_hamming_knn2_batched.  workspace: b2s_hamming_shared_workspace_bytes. */
+size_t b2s_hamming_shared_workspace_bytes(int total_tiles);
+int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
+                            const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
+                            const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
+                            int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
+                            uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* K9 — bag-of-words candidate ranking, the step in front of the relocalizer's matching (next-row #4).
  * b2s_bow_histogram_batched  replaces compute_bow_histogram (persistent_map.py:82-96) and
  *                            BoWDatabase._compute_hist (loop_closure.py:36-48) for n_frames frames at

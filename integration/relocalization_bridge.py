@@ -310,22 +310,28 @@ class BatchedMapRelocalizer:
         (map descriptors uploaded once and kept on the device).  -> (match_counts per keyframe in
         snapshot order, indices of the `top` keyframes by match count, ties to the lower frame id)."""
         import torch
-        from b200slam.frontend import PairBatch
+        from b200slam.frontend import PairBatch, SharedBlocks
 
         kfs = self.snapshot.keyframes
-        if self._map_dev is None:
+        q = np.ascontiguousarray(descriptors, dtype=np.uint8)
+        if self._map_dev is None or self._map_dev[3] < len(q):
+            # map descriptors once, followed by a slot for the query: ONE buffer, so that every block
+            # (each keyframe, and the query once instead of once per keyframe) is expanded a single time
             sizes = np.array([len(kf.descriptors) for kf in kfs], np.int64)
             off = np.zeros(len(kfs) + 1, np.int32)
             np.cumsum(sizes, out=off[1:])
-            cat = np.concatenate([np.ascontiguousarray(kf.descriptors, dtype=np.uint8) for kf in kfs], axis=0)
-            self._map_dev = (torch.from_numpy(cat).cuda(), off, torch.from_numpy(off).cuda())
-        kmap, off, off_d = self._map_dev
+            room = max(4096, len(q))
+            cat = np.concatenate([np.ascontiguousarray(kf.descriptors, dtype=np.uint8) for kf in kfs] + [np.zeros((room, 32), np.uint8)], axis=0)
+            self._map_dev = (torch.from_numpy(cat).cuda(), off, torch.from_numpy(off).cuda(), room)
+        kmap, off, off_d, _ = self._map_dev
         n = len(kfs)
-        q = np.ascontiguousarray(descriptors, dtype=np.uint8)
+        kmap[int(off[-1]):int(off[-1]) + len(q)].copy_(torch.from_numpy(q))
         q_off = (np.arange(n + 1, dtype=np.int64) * len(q)).astype(np.int32)
-        batch = PairBatch(q_desc=torch.from_numpy(q).cuda(), t_desc=kmap, q_off=torch.from_numpy(q_off).cuda(), t_off=off_d,
-                          q_off_host=q_off, t_off_host=off, q_src=torch.zeros(n, dtype=torch.int32, device="cuda"),
-                          t_src=off_d[:n].contiguous())
+        shared = SharedBlocks.build(np.concatenate([off[:-1], off[-1:]]), np.concatenate([np.diff(off), [len(q)]]),
+                                    np.full(n, n), np.arange(n), kmap.device)
+        batch = PairBatch(q_desc=kmap, t_desc=kmap, q_off=torch.from_numpy(q_off).cuda(), t_off=off_d,
+                          q_off_host=q_off, t_off_host=off, q_src=torch.full((n,), int(off[-1]), dtype=torch.int32, device="cuda"),
+                          t_src=off_d[:n].contiguous(), shared=shared)
         m = _matcher()
         keys = m.knn2(batch)
         sel = m.select(batch, keys, use_ratio=False, use_cross=True, sort_by_distance=False, max_matches=None)

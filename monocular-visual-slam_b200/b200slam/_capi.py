@@ -55,6 +55,10 @@ def _declare(lib):
     lib.b2s_hamming_knn2_batched.restype = i32
     lib.b2s_hamming_knn2_batched.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                              vp, vp, vp, i32, i32, vp, sz, vp]
+    lib.b2s_hamming_shared_workspace_bytes.restype = sz
+    lib.b2s_hamming_shared_workspace_bytes.argtypes = [i32]
+    lib.b2s_hamming_knn2_shared.restype = i32
+    lib.b2s_hamming_knn2_shared.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.b2s_hamming_set_config.restype = i32
     lib.b2s_hamming_set_config.argtypes = [i32, i32, i32]
     lib.b2s_hamming_get_config.restype = i32
@@ -110,7 +114,7 @@ EXPORTS = (
     "b2s_ransac_select", "b2s_pipe_microbench", "b2s_mma_microbench", "b2s_tmem_microbench",
     "b2s_hamming_i8_debug", "b2s_hamming_kernel_timing", "b2s_ransac_score_tc_workspace_bytes", "b2s_ransac_score_tc",
     "b2s_homography_dlt_batched", "b2s_homography_score_batched", "b2s_homography_select", "b2s_decompose_essential_batched", "b2s_refit_essential_batched", "b2s_pose_pick", "b2s_five_point_batched",
-    "b2s_bow_histogram_batched", "b2s_bow_cosine",
+    "b2s_bow_histogram_batched", "b2s_bow_cosine", "b2s_hamming_shared_workspace_bytes", "b2s_hamming_knn2_shared",
 )
 
 

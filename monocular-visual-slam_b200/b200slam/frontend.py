@@ -38,6 +38,36 @@ def _prep_desc(d) -> np.ndarray:
 
 
 @dataclass
+class SharedBlocks:
+    """Block structure of a batch whose pairs share descriptor blocks (b2s_hamming_knn2_shared):
+    block b = `rows[b]` descriptor rows starting at row `row0[b]` of the one descriptor buffer; its
+    tensor-core operand tiles start at tile `tile0[b]`; pair p's query / train side is the block
+    whose first tile is `q_xtile[p]` / `t_xtile[p]`.  Device int32 tensors + host sizes."""
+    row0: "torch.Tensor"
+    rows: "torch.Tensor"
+    tile0: "torch.Tensor"
+    q_xtile: "torch.Tensor"
+    t_xtile: "torch.Tensor"
+    n_blocks: int
+    total_tiles: int
+    max_rows: int
+
+    @staticmethod
+    def build(row0: np.ndarray, rows: np.ndarray, q_blk: np.ndarray, t_blk: np.ndarray, device) -> "SharedBlocks":
+        import torch
+
+        row0 = np.asarray(row0, np.int32)
+        rows = np.asarray(rows, np.int32)
+        tiles = (rows.astype(np.int64) + 127) // 128
+        tile0 = np.zeros(len(rows) + 1, np.int32)
+        np.cumsum(tiles, out=tile0[1:])
+        nb, npairs = len(rows), len(q_blk)
+        pack = torch.from_numpy(np.concatenate([row0, rows, tile0[:-1], tile0[np.asarray(q_blk)], tile0[np.asarray(t_blk)]]).astype(np.int32)).to(device)
+        return SharedBlocks(pack[:nb], pack[nb:2 * nb], pack[2 * nb:3 * nb], pack[3 * nb:3 * nb + npairs],
+                            pack[3 * nb + npairs:], nb, int(tile0[-1]), int(rows.max()) if nb else 0)
+
+
+@dataclass
 class PairBatch:
     """Device-resident CSR batch of (query, train) descriptor sets."""
     q_desc: "torch.Tensor"
@@ -50,6 +80,7 @@ class PairBatch:
     kp_t: "torch.Tensor | None" = None
     q_src: "torch.Tensor | None" = None
     t_src: "torch.Tensor | None" = None
+    shared: "SharedBlocks | None" = None   # pairs share descriptor blocks (frames): expand each block once
 
     @property
     def n_pairs(self) -> int:
@@ -127,9 +158,13 @@ def sequence_batch(desc_dev, kp_dev, counts: np.ndarray, first_pair: int, n_pair
     t_src = q_src + np.int32(frame_rows)
     pack = torch.from_numpy(np.concatenate([q_off, t_off, q_src, t_src])).to(dev)
     n1 = n_pairs + 1
+    # frames first_pair .. first_pair + n_pairs are the blocks; pair p = (block p, block p + 1)
+    frames = np.arange(first_pair, first_pair + n_pairs + 1, dtype=np.int64)
+    shared = SharedBlocks.build((frames * frame_rows).astype(np.int32), counts[first_pair:first_pair + n_pairs + 1],
+                                np.arange(n_pairs), np.arange(1, n_pairs + 1), dev)
     return PairBatch(q_desc=desc_dev, t_desc=desc_dev, q_off=pack[:n1], t_off=pack[n1:2 * n1],
                      q_off_host=q_off, t_off_host=t_off, kp_q=kp_dev, kp_t=kp_dev,
-                     q_src=pack[2 * n1:2 * n1 + n_pairs], t_src=pack[2 * n1 + n_pairs:])
+                     q_src=pack[2 * n1:2 * n1 + n_pairs], t_src=pack[2 * n1 + n_pairs:], shared=shared)
 
 
 @dataclass
@@ -172,6 +207,17 @@ class HammingMatcher:
         fs = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
         bb = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
         ws_ptr, ws_bytes = None, 0
+        sh = b.shared
+        if sh is not None and self.variant == _capi.VARIANT_I8MMA1 and nq > 0 and nt > 0 and b.q_desc.data_ptr() == b.t_desc.data_ptr():
+            # pairs share descriptor blocks (frames): every block is expanded once
+            ws_bytes = int(self._lib.b2s_hamming_shared_workspace_bytes(sh.total_tiles))
+            if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(self._lib.b2s_hamming_knn2_shared(
+                ptr(b.q_desc), ptr(sh.row0), ptr(sh.rows), ptr(sh.tile0), sh.n_blocks, sh.total_tiles, sh.max_rows,
+                ptr(sh.q_xtile), ptr(sh.t_xtile), ptr(b.q_off), ptr(b.t_off), b.n_pairs, nq, nt, b.max_nq, b.max_nt,
+                ptr(fb), ptr(fs), ptr(bb), self._ws.data_ptr(), ws_bytes, current_stream()))
+            return Keys(fb[:nq], fs[:nq], bb[:nt])
         if nq > 0 and (self.variant != _capi.VARIANT_POPC or self.t_split != 1):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             want = self.t_split if self.t_split > 1 else max(1, min(64, (4 * sms) // max(1, b.n_pairs)))

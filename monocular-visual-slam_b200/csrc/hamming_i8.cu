@@ -81,18 +81,23 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
 __global__ void __launch_bounds__(128) expand_pm8_kernel(const uint8_t* __restrict__ desc,
                                                          const int32_t* __restrict__ off,
                                                          const int32_t* __restrict__ src, int tiles_per_pair,
-                                                         int train, int layout, uint4* __restrict__ out) {
+                                                         int train, int layout, uint4* __restrict__ out,
+                                                         const int32_t* __restrict__ blk_rows,
+                                                         const int32_t* __restrict__ blk_tile0) {
   // one CTA per (tile, pair), one thread per row: the row's 32 bytes are read once (2 x LDG.128)
   // and its 17 / 18 k-chunks leave as STG.128 that are contiguous across the 128 threads.
   const int chunks = (layout == 1 || layout == 3) ? kI8Chunks + 1 : kI8Chunks;
   const int pair = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
-  const int o = off[pair];
-  const int n = off[pair + 1] - o;
+  // block mode (blk_rows != nullptr): "pair" is a descriptor BLOCK (a frame) shared by several pairs:
+  // blk_rows[b] rows starting at input row src[b], expanded once to tiles blk_tile0[b] ...
+  const int o = blk_rows ? 0 : off[pair];
+  const int n = blk_rows ? blk_rows[pair] : off[pair + 1] - o;
   if (tile * kI8Tile >= n) return;  // tile never read
   const int in0 = src ? src[pair] : o;
   const int row = tile * kI8Tile + r;
   const bool valid = row < n;
-  uint4* dst = out + ((size_t)pair * tiles_per_pair + tile) * (size_t)(chunks * kI8Tile) + r;
+  const size_t tile_idx = blk_rows ? (size_t)blk_tile0[pair] + tile : (size_t)pair * tiles_per_pair + tile;
+  uint4* dst = out + tile_idx * (size_t)(chunks * kI8Tile) + r;
   uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
   if (valid) {
     const uint4* p = reinterpret_cast<const uint4*>(desc + (size_t)(in0 + row) * B2S_DESC_BYTES);
@@ -263,6 +268,8 @@ struct I8Params {
   uint32_t* __restrict__ fwd_second;
   uint32_t* __restrict__ bwd_best;
   int q_tiles, t_tiles, n_pairs;
+  const int32_t* __restrict__ q_xt;  // optional (shared blocks): first expanded tile of each pair's query / train side,
+  const int32_t* __restrict__ t_xt;  // both in the ONE unified buffer qx == tx; nullptr = pair * q_tiles / pair * t_tiles
   unsigned long long* dbg;  // optional per-CTA stall counters (b2s_hamming_i8_debug), else nullptr
   int mode;                 // diagnostics only: bit 0 = epilogue does no work, bit 1 = ring is loaded once,
                             // (single-product kernel) bit 2 = no column butterfly, bit 3 = no row top-2
@@ -710,8 +717,10 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         // index chunk), a train slot chunks 0..15 and chunk 17 (its B-side index chunk)
         constexpr uint32_t kTStride = EPI == 1 ? (uint32_t)kI8sQTileBytes : (uint32_t)kI8TileBytes;
         constexpr uint32_t kQBytes = EPI == 1 ? (uint32_t)kI8TileBytes : (uint32_t)kI8sQTileBytes;
-        const uint8_t* tsrc = p.tx + (size_t)pair * p.t_tiles * kTStride;
-        const uint8_t* qsrc = p.qx + ((size_t)pair * p.q_tiles + 2 * qb) * kI8sQTileBytes;
+        const size_t t_tile0 = p.t_xt ? (size_t)p.t_xt[pair] : (size_t)pair * p.t_tiles;
+        const size_t q_tile0 = p.q_xt ? (size_t)p.q_xt[pair] : (size_t)pair * p.q_tiles;
+        const uint8_t* tsrc = p.tx + t_tile0 * kTStride;
+        const uint8_t* qsrc = p.qx + (q_tile0 + 2 * qb) * kI8sQTileBytes;
         for (int t = 0; t < n_tt; ++t, ++tau) {
           const uint32_t s = tau % kI8Stages, g = 2u * tau;
           uint64_t* go_a = &b_go[g % kI8sGo];
@@ -1307,10 +1316,10 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   uint8_t* qx = static_cast<uint8_t*>(workspace);
   uint8_t* tx = qx + (size_t)n_pairs * qt * q_units * 16;
   expand_pm8_kernel<<<dim3(qt, n_pairs), 128, 0, st>>>(q, q_off, q_src, qt, 0, unified ? 3 : single ? 1 : 0,
-                                                                               reinterpret_cast<uint4*>(qx));
+                                                                               reinterpret_cast<uint4*>(qx), nullptr, nullptr);
   B2S_CUDA(cudaGetLastError());
   expand_pm8_kernel<<<dim3(tt, n_pairs), 128, 0, st>>>(t, t_off, t_src, tt, 1, unified ? 3 : single ? 2 : 0,
-                                                                                reinterpret_cast<uint4*>(tx));
+                                                                                reinterpret_cast<uint4*>(tx), nullptr, nullptr);
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
   static bool attr_set = false;
@@ -1330,6 +1339,8 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.q_tiles = qt;
   p.t_tiles = tt;
   p.n_pairs = n_pairs;
+  p.q_xt = nullptr;
+  p.t_xt = nullptr;
   p.dbg = g_i8_dbg;
   p.mode = g_i8_mode;
   if (single) {
@@ -1358,6 +1369,68 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
   if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
   hamming_knn2_i8_kernel<<<grid, kI8Threads, kI8SmemBytes, st>>>(p);
+  B2S_CUDA(cudaGetLastError());
+  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
+  note_launch();
+  return B2S_OK;
+}
+
+size_t hamming_i8_shared_workspace_bytes(int total_tiles) { return (size_t)total_tiles * kI8sQTileBytes; }
+
+// Batches whose pairs share descriptor blocks (frames): every block is expanded ONCE into unified
+// tiles, the pairs address them through q_xtile / t_xtile.  Single-product kernel, 16x256b epilogue.
+int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
+                             const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
+                             const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
+                             int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
+                             uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
+                             cudaStream_t st) {
+  B2S_REQUIRE(n_blocks <= 65535, "n_blocks %d exceeds grid.y limit 65535; split the batch", n_blocks);
+  if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
+  if (total_nq > 0) {
+    B2S_CUDA(cudaMemsetAsync(fwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+    B2S_CUDA(cudaMemsetAsync(fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+  }
+  if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0 || n_blocks == 0) return B2S_OK;
+  const size_t need = hamming_i8_shared_workspace_bytes(total_tiles);
+  B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+              "shared-block Hamming needs %zu workspace bytes (b2s_hamming_shared_workspace_bytes), got %zu", need,
+              workspace_bytes);
+  B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
+  const int bt = (max_block_rows + kI8Tile - 1) / kI8Tile;
+  uint8_t* x = static_cast<uint8_t*>(workspace);
+  expand_pm8_kernel<<<dim3(bt, n_blocks), 128, 0, st>>>(desc, nullptr, blk_row0, 0, 0, 3, reinterpret_cast<uint4*>(x),
+                                                       blk_rows, blk_tile0);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kI8sSmemBytes));
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kI8sSmemBytes));
+    attr_set = true;
+  }
+  I8Params p;
+  p.qx = x;
+  p.tx = x;
+  p.q_off = q_off;
+  p.t_off = t_off;
+  p.fwd_best = fwd_best;
+  p.fwd_second = fwd_second;
+  p.bwd_best = bwd_best;
+  p.q_tiles = (max_nq + kI8Tile - 1) / kI8Tile;
+  p.t_tiles = (max_nt + kI8Tile - 1) / kI8Tile;
+  p.n_pairs = n_pairs;
+  p.q_xt = q_xtile;
+  p.t_xt = t_xtile;
+  p.dbg = g_i8_dbg;
+  p.mode = g_i8_mode & ~16;
+  const long items = (long)((p.q_tiles + 1) / 2) * n_pairs;
+  const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
+  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
+  if (p.dbg) hamming_knn2_i8s_kernel<1, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
+  else hamming_knn2_i8s_kernel<1, false><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
   B2S_CUDA(cudaGetLastError());
   if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
   note_launch();

@@ -243,3 +243,39 @@ def test_i8_variant_pipeline_front_doors(hg, matcher_i8):
         np.testing.assert_array_equal(qi, hg[key + "_q"], err_msg=key)
         np.testing.assert_array_equal(ti, hg[key + "_t"], err_msg=key)
         np.testing.assert_array_equal(d, hg[key + "_d"], err_msg=key)
+
+
+def test_shared_block_path_equals_per_pair_expansion():
+    """b2s_hamming_knn2_shared (every frame expanded once, pairs address the tiles) against the
+    per-pair expansion and against the POPC kernel on a ragged frame sequence: tile-edge sizes, a
+    one-row frame and an empty frame."""
+    import dataclasses
+    import torch
+    from b200slam import _capi
+    from b200slam.frontend import HammingMatcher, sequence_batch
+    rng = np.random.default_rng(77)
+    N = 320
+    counts = np.array([300, 1, 128, 0, 257, 129, 320, 127], np.int32)
+    F = len(counts)
+    desc = rng.integers(0, 4, (F * N, 32), dtype=np.uint8)          # tie-heavy
+    desc[2 * N:2 * N + 64] = desc[:64]                               # duplicates across frames
+    dev = torch.from_numpy(desc).cuda()
+    kp = torch.zeros((F * N, 2), dtype=torch.float32, device="cuda")
+    b = sequence_batch(dev, kp, counts, 0, F - 1, N)
+    assert b.shared is not None and b.shared.n_blocks == F
+    shared = HammingMatcher(variant=_capi.VARIANT_I8MMA1).knn2(b)
+    plain = HammingMatcher(variant=_capi.VARIANT_I8MMA1).knn2(dataclasses.replace(b, shared=None))
+    popc = HammingMatcher(variant=_capi.VARIANT_POPC).knn2(b)
+    for name in ("fwd_best", "fwd_second", "bwd_best"):
+        a, c, d = (getattr(x, name).cpu().numpy() for x in (shared, plain, popc))
+        assert np.array_equal(a, c), name
+        assert np.array_equal(a, d), name
+    # and against the oracle, pair by pair
+    fb, fs, bw = (getattr(shared, n).cpu().numpy().view(np.uint32) for n in ("fwd_best", "fwd_second", "bwd_best"))
+    for p in range(F - 1):
+        q = desc[p * N:p * N + counts[p]]
+        t = desc[(p + 1) * N:(p + 1) * N + counts[p + 1]]
+        rb, rs, rw = ho.packed_keys(q, t)
+        qo, to = int(b.q_off_host[p]), int(b.t_off_host[p])
+        assert np.array_equal(fb[qo:qo + len(q)], rb) and np.array_equal(fs[qo:qo + len(q)], rs), p
+        assert np.array_equal(bw[to:to + len(t)], rw), p
