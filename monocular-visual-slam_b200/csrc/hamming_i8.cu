@@ -62,8 +62,8 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib, bool train) {
 // layout 3 (shipped, 16x256b epilogue): UNIFIED tiles, 18 chunks, the same tile serves a frame as query
 // and as train operand.  Data: bit clear / set -> +8 / -8 on both sides, so the 8 data K-steps give
 // 64 (256 - 2 ham) = 2^14 - 128 ham: the accumulator DEcreases with the distance.  The index K-step
-// multiplies the query tile's chunk 16 with the train tile's chunk 17:
-//     A (chunk 16) [-1, r, 127, 127, 127, 127, 2, 0..]     B (chunk 17) [c, -1, 127, 127, 127, 6, 1, 0..]
+// multiplies the query tile's chunk 17 with the train tile's chunk 16:
+//     A (chunk 17) [-1, r, 127, 127, 127, 127, 2, 0..]     B (chunk 16) [c, -1, 127, 127, 127, 6, 1, 0..]
 // = -c - r + 3 * 16129 + 762 + 2 = 49151 - c - r, so that  acc = 65535 - (128 ham + c + r) = ~key:
 // the COMPLEMENT of the 16-bit key of layouts 1 / 2.  The epilogue takes maxima instead of minima
 // and complements its few results.  Padding rows are all zero on both sides: acc = 0, below every
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(128) expand_pm8_kernel(const uint8_t* __restri
   }
   uint4 v;
   if (layout == 3) {
-    // unified tile: chunk 16 = index chunk of the row as a QUERY row (A side), chunk 17 = as a TRAIN row
-    // (B side); padding rows are all zero.  See the 16x256b epilogue for the arithmetic.
+    // unified tile: chunk 16 = index chunk of the row as a TRAIN row (B side; a train slot is then ONE
+    // contiguous 34 KB copy), chunk 17 = as a QUERY row (A side); padding rows are all zero.  See the 16x256b epilogue for the arithmetic.
     const uint32_t rr = (uint32_t)r;
-    dst[16 * kI8Tile] = valid ? make_uint4(0x7F7F00FFu | (rr << 8), 0x00027F7Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    dst[17 * kI8Tile] = valid ? make_uint4(0x7F7FFF00u | rr, 0x0001067Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    dst[17 * kI8Tile] = valid ? make_uint4(0x7F7F00FFu | (rr << 8), 0x00027F7Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    dst[16 * kI8Tile] = valid ? make_uint4(0x7F7FFF00u | rr, 0x0001067Fu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     return;
   }
   if (layout == 0) {
@@ -713,8 +713,9 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         if (q0 >= nq || nt == 0) continue;
         const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
         const bool has_b = q0 + kI8Tile < nq;
-        // EPI 1: unified 18-chunk tiles on both sides; a query slot takes chunks 0..16 (data + its A-side
-        // index chunk), a train slot chunks 0..15 and chunk 17 (its B-side index chunk)
+        // EPI 1: unified 18-chunk tiles on both sides; a train slot takes chunks 0..16 (data + its B-side
+        // index chunk, one copy), a query slot chunks 0..15 and chunk 17 (its A-side index chunk, two copies
+        // once per item)
         constexpr uint32_t kTStride = EPI == 1 ? (uint32_t)kI8sQTileBytes : (uint32_t)kI8TileBytes;
         constexpr uint32_t kQBytes = EPI == 1 ? (uint32_t)kI8TileBytes : (uint32_t)kI8sQTileBytes;
         const size_t t_tile0 = p.t_xt ? (size_t)p.t_xt[pair] : (size_t)pair * p.t_tiles;
@@ -732,25 +733,27 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           if (t == 0) {
             if (n >= 1) mbar_wait_bounded(&b_qempty[0], (n - 1u) & 1u);
             mbar_arrive_expect_tx(go_a, kQBytes + (skip_t ? 0 : kI8TileBytes));
-            bulk_g2s(s_q, qsrc, kQBytes, go_a);
+            if (EPI == 1) {
+              bulk_g2s(s_q, qsrc, 16 * kI8ChunkBytes, go_a);
+              bulk_g2s(s_q + 16 * kI8ChunkBytes, qsrc + 17 * kI8ChunkBytes, kI8ChunkBytes, go_a);
+            } else {
+              bulk_g2s(s_q, qsrc, kQBytes, go_a);
+            }
           } else if (skip_t) {
             mbar_arrive(go_a);
           } else {
             mbar_arrive_expect_tx(go_a, kI8TileBytes);
           }
-          if (!skip_t) {
-            if (EPI == 1) {
-              bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kTStride, 16 * kI8ChunkBytes, go_a);
-              bulk_g2s(s_t + (size_t)s * kI8TileBytes + 16 * kI8ChunkBytes, tsrc + (size_t)t * kTStride + 17 * kI8ChunkBytes,
-                       kI8ChunkBytes, go_a);
-            } else {
-              bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kI8TileBytes, kI8TileBytes, go_a);
-            }
-          }
+          if (!skip_t) bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kTStride, kI8TileBytes, go_a);
           if (t == 0 && has_b) {
             if (n >= 1) mbar_wait_bounded(&b_qempty[1], (n - 1u) & 1u);
             mbar_arrive_expect_tx(go_b, kQBytes);
-            bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kQBytes, go_b);
+            if (EPI == 1) {
+              bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, 16 * kI8ChunkBytes, go_b);
+              bulk_g2s(s_q + kI8sQTileBytes + 16 * kI8ChunkBytes, qsrc + kI8sQTileBytes + 17 * kI8ChunkBytes, kI8ChunkBytes, go_b);
+            } else {
+              bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kQBytes, go_b);
+            }
           } else {
             mbar_arrive(go_b);
           }
