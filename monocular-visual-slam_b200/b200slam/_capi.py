@@ -34,7 +34,9 @@ class B2SError(RuntimeError):
 
 
 def lib_path() -> Path:
-    return Path(__file__).resolve().parent / _LIB_NAME
+    """libb2s.so next to this module; B2S_LIB overrides it (diagnostic builds only, e.g. tools/k3h_check.py)."""
+    override = os.environ.get("B2S_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / _LIB_NAME
 
 
 def _declare(lib):

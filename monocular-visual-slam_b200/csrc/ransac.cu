@@ -70,12 +70,17 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 // data) is re-evaluated in float64 by the same thread with the very expression of K3, so the
 // counts equal the float64 kernel's counts while the FP64 pipe (half the FP32 rate on B200, and
 // 2 issue cycles per instruction) is out of the inner loop.
-//   u = 2^-24.  With nE = ||E||_F (float32 copy), W1 = max ||x1||, W2 = max ||x2|| over the pair:
-//   |a_i - fl(a_i)| <= 4u nE W1 =: eta1, |b_j - fl(b_j)| <= 4u nE W2 =: eta2   (E rounding + 2 FMAs)
-//   |num - fl(num)| <= 8u nE W1 W2 =: delta                      (3 more roundings on |x2|.|E x1|)
-//   |den - fl(den)| <= 8u den + 4 nE (W1 eta1 + W2 eta2) + 2 (eta1^2 + eta2^2)
-//   |d - fl(d)|     <= 2 |num| delta + delta^2 + th^2 |den - fl(den)| + 4u (num^2 + th^2 den)
-// B below takes every constant 2x larger than that.
+//   u = 2^-24; e = fl32(E); nE = ||e||_F, W1 = max ||(x1, 1)||, W2 = max ||(x2, 1)|| over the pair; the
+//   points are float32 already, so only E is rounded on input.  With r_i / c_j the row / column norms of E:
+//   a_i = fma(e_i0, x, fma(e_i1, y, e_i2)):  |a_i - fl(a_i)| <= u (2|E_i0 x| + 3|E_i1 y| + 3|E_i2|) <= 3u r_i W1
+//   (one input rounding per term + two FMA roundings, Cauchy-Schwarz), likewise |b_j - fl(b_j)| <= 3u c_j W2;
+//   num = fma(u, a0, fma(v, a1, a2)):  the a-errors give <= 3u W1 W2 nE, the two FMA roundings <= 2u W2 nE W1:
+//       |num - fl(num)| <= 5u nE W1 W2 =: delta;
+//   den (four non-negative terms, nested FMAs):  |den - fl(den)| <= 6u nE^2 (W1^2 + W2^2) + 4u den;
+//   T = fl(fl32(th^2) den), d = fma(num, num, -T):
+//       |d - fl(d)| <= 2 |num| delta + delta^2 + 6u th^2 nE^2 (W1^2 + W2^2) + 7u (num^2 + T)
+//   (all to first order in u; the float64 kernel's own rounding is 9 orders of magnitude below).
+//   B below takes 7u, 9u and 10u for the 5u, 6u and 7u (1.4x), and every norm is nudged up by 1e-4.
 constexpr int kScoreHThreads = 128;
 constexpr int kScoreHChunk = 256;   // 4 KB of shared memory: small enough to co-reside with the 220 KB K2s CTA of another stream
 
@@ -127,11 +132,13 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   __syncthreads();
   constexpr float kU = 5.9604645e-8f * 1.0001f;                     // 2^-24, nudged up: the bound itself is rounded
   const float nE = sqrtf(n2) * 1.0001f, W1 = sqrtf(s_w[0]) * 1.0001f, W2 = sqrtf(s_w[1]) * 1.0001f;
-  const float eta1 = 8.0f * kU * nE * W1, eta2 = 8.0f * kU * nE * W2;
-  const float delta = 16.0f * kU * nE * W1 * W2;
+#ifndef B2S_K3H_BOUND_SCALE
+#define B2S_K3H_BOUND_SCALE 1.0f   // diagnostics only (tools/k3h_check.py): < 1 shrinks the band below what is proven
+#endif
+  const float delta = B2S_K3H_BOUND_SCALE * 7.0f * kU * nE * W1 * W2;
   const float two_delta_raw = 2.0f * delta;
-  const float c0_raw = delta * delta + th2 * (8.0f * nE * (W1 * eta1 + W2 * eta2) + 4.0f * (eta1 * eta1 + eta2 * eta2));
-  const float rho = 24.0f * kU;                                     // relative part, applied to num^2 + th^2 den
+  const float c0_raw = delta * delta + th2 * (B2S_K3H_BOUND_SCALE * 9.0f * kU * nE * nE * (W1 * W1 + W2 * W2));
+  const float rho = B2S_K3H_BOUND_SCALE * 10.0f * kU;                                     // relative part, applied to num^2 + th^2 den
   // The loop does not form q = num^2 on its own: with q + T = d + 2T the relative part is
   // rho (q + T) <= rho |d| + 2 rho T, so |d| > B is implied by |d| (1 - rho) > 2 delta |num| + 2 rho T + c0,
   // i.e. by |d| > (1 + 2 rho)(2 delta |num| + 2 rho T + c0).  The three coefficients below carry that
