@@ -364,16 +364,16 @@ def b200_main(a):
     t_stage = variants_ms[shipped] * 1e-3                       # memsets + 2 expand launches + kernel
     t_i8 = (float(np.mean(kern_ms)) * 1e-3) if kern_ms else t_stage
     # DRAM traffic of one launch of the shipped kernel, from the ncu --set full capture in profiles/
-    traffic = {"i8s": 352.0e6, "i8": 399.7e6}.get(shipped)
+    traffic = {"i8s": 185.3e6, "i8": 399.7e6}.get(shipped)
     roof = {"bound": "tensor", "achieved": i8_ops / t_i8 / 1e12, "peak": i8_peak / 1e12, "unit": "TOP/s (int8)",
             "frac": i8_ops / t_i8 / i8_peak, "traffic": traffic,
             "kernel": {"i8s": "hamming_knn2_i8s_kernel", "i8": "hamming_knn2_i8_kernel"}[shipped],
             "kernel_ms": t_i8 * 1e3, "algorithmic_int8_ops_per_launch": i8_ops,
-            "stage": {"what": "whole b2s_hamming_knn2_batched call: 3 memsets + 2 expand_pm8_kernel launches + the kernel",
+            "stage": {"what": "whole Hamming call (b2s_hamming_knn2_shared for the shipped variant: 3 memsets + ONE expand_pm8_kernel launch over the frames + the kernel; the other variants expand per pair and side)",
                       "ms": t_stage * 1e3, "frac": i8_ops / t_stage / i8_peak},
             "peak_source": "b2s_mma_microbench measured in this run (dense tcgen05.mma kind::i8 M128.N128.K32 from shared memory); "
                            "2 x MEASURED_PEAKS bf16 would be %.0f TOP/s" % (2.0 * bf16_peak),
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_final2_ncu.md",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_final3_ncu.md",
             "note": "algorithmic = ONE 2*256*Nq*Nt int8 contraction per frame pair (SURVEY 8d); the kernel issues 9 K-steps per 8 of "
                     "data (the 9th adds the row/column index), and the two-product variant i8 issues the contraction twice",
             "hamming_variants_ms": variants_ms,
