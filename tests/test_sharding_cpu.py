@@ -53,3 +53,24 @@ def test_gather_world2_gloo(n_items):
     ids = np.arange(n_items)
     np.testing.assert_array_equal(got, pack_records(ids, ids * 3 + 1, ids % 5, ids * 2))
     assert got.shape == (n_items, RECORD_WIDTH)
+
+
+def test_shared_block_tables():
+    """SharedBlocks.build (b2s_hamming_knn2_shared): tile prefix sums and per-pair first tiles for a
+    frame sequence (pair p = frames p, p+1) and for a one-query-vs-map sweep — pure index arithmetic."""
+    import numpy as np
+    import torch
+    from b200slam.frontend import SharedBlocks
+    rows = np.array([300, 1, 128, 0, 257, 129], np.int32)
+    row0 = (np.arange(6) * 320).astype(np.int32)
+    sb = SharedBlocks.build(row0, rows, np.arange(5), np.arange(1, 6), torch.device("cpu"))
+    tiles = [3, 1, 1, 0, 3, 2]
+    assert sb.n_blocks == 6 and sb.total_tiles == sum(tiles) and sb.max_rows == 300
+    assert sb.tile0.tolist() == [0, 3, 4, 5, 5, 8]
+    assert sb.q_xtile.tolist() == [0, 3, 4, 5, 5] and sb.t_xtile.tolist() == [3, 4, 5, 5, 8]
+    assert sb.row0.tolist() == row0.tolist() and sb.rows.tolist() == rows.tolist()
+    # sweep: blocks = keyframes..., query last; every pair's query side is the last block
+    rows = np.array([130, 128, 5, 2000], np.int32)
+    sb = SharedBlocks.build(np.array([0, 130, 258, 263], np.int32), rows, np.full(3, 3), np.arange(3), torch.device("cpu"))
+    assert sb.tile0.tolist() == [0, 2, 3, 4] and sb.total_tiles == 4 + 16
+    assert sb.q_xtile.tolist() == [4, 4, 4] and sb.t_xtile.tolist() == [0, 2, 3]
