@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
       if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
       const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
       const int rows_valid = max(0, min(kI8Tile, nq - q0));
-      const bool staged = (to & 3) == 0;
+      const bool staged = (reinterpret_cast<uintptr_t>(p.bwd_best + to) & 15u) == 0;   // cp.async.cg moves 16 aligned bytes
       uint32_t gbest = kNone, gsecond = kNone;
       // this set's tile pairs: g = g_item + 2 t + sub with g % 4 == set, i.e. every other train tile
       for (int t = (int)(((set >> 1) ^ (g_item >> 1)) & 1u); t < n_tt; t += 2) {
@@ -970,8 +970,8 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         // Holding them in registers through the top-2 costs more than it saves (96 registers, 64 of them
         // accumulator), and loading them late leaves the L2 latency exposed (10 % of the epilogue's
         // samples sat on the first compare): cp.async parks them in this lane's shared-memory slot
-        // before the accumulator wait.  (.cg needs 16-byte alignment: a pair whose train offset is not
-        // a multiple of 4 rows takes the plain loads below.)
+        // before the accumulator wait.  (.cg needs 16-byte alignment: a pair whose slice of bwd_best does
+        // not start on a 16-byte boundary takes the plain loads below.)
         uint4* cur_slot = s_cur + (warp - 2) * 32 + lane;
         if (staged) {
           const int left = nt - tbase - 4 * lane;   // valid rows from this lane's first column on
@@ -1298,16 +1298,25 @@ size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
   return (size_t)n_pairs * (qt + tt) * kI8sQTileBytes;  // sized for the largest layout (unified 18-chunk tiles on both sides)
 }
 
+// every key starts as "none".  Three separate memset nodes on purpose: ONE 7 MB memset over the (often
+// adjacent) arrays, or a fill kernel, is 1 % faster for a lone step but changed how two steps in flight
+// interleave and cost the end-to-end path 8 % (439k -> 403k pairs/s, A/B on one box).
+static int clear_keys(uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, int total_nq, int total_nt,
+                      cudaStream_t st) {
+  if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
+  if (total_nq > 0) {
+    B2S_CUDA(cudaMemsetAsync(fwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+    B2S_CUDA(cudaMemsetAsync(fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+  }
+  return B2S_OK;
+}
+
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
                       size_t workspace_bytes, int single, cudaStream_t st) {
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
-  if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
-  if (total_nq > 0) {  // rows of pairs without train descriptors keep "none"
-    B2S_CUDA(cudaMemsetAsync(fwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
-    B2S_CUDA(cudaMemsetAsync(fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
-  }
+  if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;  // rows of pairs without train descriptors keep "none"
   if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0) return B2S_OK;
   const int qt = (max_nq + kI8Tile - 1) / kI8Tile, tt = (max_nt + kI8Tile - 1) / kI8Tile;
   const size_t need = hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
@@ -1389,11 +1398,7 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
                              uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
                              cudaStream_t st) {
   B2S_REQUIRE(n_blocks <= 65535, "n_blocks %d exceeds grid.y limit 65535; split the batch", n_blocks);
-  if (total_nt > 0) B2S_CUDA(cudaMemsetAsync(bwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nt, st));
-  if (total_nq > 0) {
-    B2S_CUDA(cudaMemsetAsync(fwd_best, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
-    B2S_CUDA(cudaMemsetAsync(fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
-  }
+  if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;
   if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0 || n_blocks == 0) return B2S_OK;
   const size_t need = hamming_i8_shared_workspace_bytes(total_tiles);
   B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
