@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--chunks", type=int, default=1, help="e2e: copy/compute overlap chunks")
     ap.add_argument("--scoring", default="cuda", choices=["tc", "cuda"], help="RANSAC scoring: K3t tensor cores or K3h CUDA cores (same counts)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="e2e: steps in flight (device/pinned buffer sets)")
+    ap.add_argument("--e2e-mode", default="graphs", choices=["single", "graphs"],
+                    help="e2e: 'graphs' = one whole-step graph per tracker and stream (default, 437k pairs/s); "
+                         "'single' = SequencePipeline, one kernel stream with overlapping copies (427k, interleave-proof)")
     ap.add_argument("--no-graph", action="store_true", help="e2e: launch eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--sweep", action="store_true", help="also time every POPC-kernel configuration (extra key)")
     return ap.parse_args()
@@ -304,31 +307,48 @@ def b200_main(a):
     stages = stage_times()
 
     # ---- end to end through host buffers: pinned host frames -> device -> kernels -> pinned host ----
-    # Two trackers (own device buffers, own pinned result buffers, own CUDA graph) alternate on two
-    # streams, so the upload of step s+1 overlaps the kernels of step s.  EVERY step uploads its
-    # frames (23.8 MB) and downloads its results (1.9 MB) inside the timed region; one event pair
-    # brackets all K steps (with the steps overlapping there is no per-step time to add up).
+    # EVERY step uploads its frames (23.8 MB) and downloads its results (1.9 MB) inside the timed region;
+    # one event pair brackets all K steps (with the steps overlapping there is no per-step time to add up).
+    # Default ("graphs"): one whole-step CUDA graph (uploads, kernels, downloads on three streams) per
+    # tracker, `depth` trackers on their own streams: the upload of step s+1 overlaps the kernels of step
+    # s, and so may the first / last kernels of neighbouring steps (which hides the graph launch gaps).
+    # "single": SequencePipeline — copies overlap, but all kernels run on ONE stream and never interleave
+    # across steps: 2 % slower here (the 20 us between back-to-back graph launches show), immune to the
+    # interleaving lottery (a different memset scheme once cost the graphs mode 8 %).
     depth = max(1, a.e2e_depth)
-    trackers = [SequenceTracker(a.pairs + 1, a.nfeat, cfg, variant=variant, chunks=a.chunks, device=dev, use_graph=not a.no_graph)
-                for _ in range(depth)]
-    streams = [torch.cuda.Stream(dev) for _ in range(depth)]
-    tracker = trackers[0]
-    gather_small = None
-    if world > 1:
-        lo, hi = tracker.bounds[-1]
-        gather_small = [torch.empty((world * (hi - lo), 4), dtype=torch.int32, device=dev) for _ in range(depth)]
+    from b200slam.frontend import SequencePipeline
+    if a.e2e_mode == "single":
+        pipe = SequencePipeline(a.pairs + 1, a.nfeat, cfg, variant=variant, depth=depth, device=dev, use_graph=not a.no_graph)
+        tracker, e2e_streams, n_chunks = pipe, list(pipe.streams()), 1
+        gather_small = torch.empty((world * a.pairs, 4), dtype=torch.int32, device=dev) if world > 1 else None
 
-    def e2e_step(i):
-        tr = trackers[i % depth]
-        with torch.cuda.stream(streams[i % depth]):
-            tr.run(desc_host, kp_host, counts)
-            if world > 1:
-                last = tr._keep[-1]
-                rec = torch.stack([last.sel.count, last.best_h, last.best_count, pair_ids[: last.best_h.numel()]], dim=1).contiguous()
-                dist.all_gather_into_tensor(gather_small[i % depth], rec)
+        def _gather(res):                                          # runs on the kernel stream, after the step's graph
+            rec = torch.stack([res.sel.count, res.best_h, res.best_count, pair_ids], dim=1).contiguous()
+            dist.all_gather_into_tensor(gather_small, rec)
+
+        def e2e_step(i):
+            pipe.submit(desc_host, kp_host, counts, after_compute=_gather if world > 1 else None)
+    else:
+        trackers = [SequenceTracker(a.pairs + 1, a.nfeat, cfg, variant=variant, chunks=a.chunks, device=dev, use_graph=not a.no_graph)
+                    for _ in range(depth)]
+        e2e_streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        tracker, n_chunks = trackers[0], len(trackers[0].bounds)
+        gather_small = None
+        if world > 1:
+            lo, hi = tracker.bounds[-1]
+            gather_small = [torch.empty((world * (hi - lo), 4), dtype=torch.int32, device=dev) for _ in range(depth)]
+
+        def e2e_step(i):
+            tr = trackers[i % depth]
+            with torch.cuda.stream(e2e_streams[i % depth]):
+                tr.run(desc_host, kp_host, counts)
+                if world > 1:
+                    last = tr._keep[-1]
+                    rec = torch.stack([last.sel.count, last.best_h, last.best_count, pair_ids[: last.best_h.numel()]], dim=1).contiguous()
+                    dist.all_gather_into_tensor(gather_small[i % depth], rec)
 
     def e2e_timed(steps, warmup):
-        for i in range(max(warmup, 2 * depth)):                # eager pass + graph capture for every tracker
+        for i in range(max(warmup, 2 * depth)):                # eager pass + graph capture for every buffer set
             e2e_step(i)
             torch.cuda.synchronize()
         if world > 1:
@@ -337,11 +357,11 @@ def b200_main(a):
         main = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
-        for st in streams:
+        for st in e2e_streams:
             st.wait_event(e0)
         for i in range(steps):
             e2e_step(i)
-        for st in streams:
+        for st in e2e_streams:
             main.wait_stream(st)
         e1.record(main)
         torch.cuda.synchronize()
@@ -414,7 +434,7 @@ def b200_main(a):
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 (+-8 contraction of u8 bit vectors, exact) + f64 Sampson", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clk, "roofline": roof,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": len(tracker.bounds), "cuda_graph": not a.no_graph, "steps_in_flight": depth,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tracker.h2d_bytes, "d2h_bytes_per_step": tracker.d2h_bytes, "chunks": n_chunks, "cuda_graph": not a.no_graph, "steps_in_flight": depth, "pipeline": a.e2e_mode,
                     "timing": "one CUDA-event pair around all K steps (steps overlap); inputs arrive over PCIe every step",
                     "cpu_affinity_first_count": numa,
                     "ms_per_step": e2e_total / a.steps},

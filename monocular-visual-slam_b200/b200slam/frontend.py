@@ -555,9 +555,8 @@ class FrontendConfig:
     precision: int = 64
     seed: int = 1337
     with_pose: bool = False    # also refit E on the winner's inliers and recover (R, t) on the device (K7)
-    scoring: str = "cuda"      # "cuda": K3h on the CUDA cores (default); "tc": K3t tensor-core scoring.  Same counts; K3t is 8 %
-                               # faster alone but, as a second 220 KB-shared-memory persistent kernel, overlaps worse with K2s
-                               # when two steps are in flight (bench e2e 281k vs 326k pairs/s)
+    scoring: str = "cuda"      # "cuda": K3h on the CUDA cores (default, 0.30 ms per 296-pair step); "tc": K3t tensor-core
+                               # scoring (0.35 ms).  Same counts.
 
 
 @dataclass
@@ -711,6 +710,113 @@ class SequenceTracker:
         main.wait_stream(self.s_down)
         self._keep = keep                                          # device tensors stay alive until the next run
         return self.out
+
+
+class SequencePipeline:
+    """End-to-end consecutive-frame tracking from pinned host buffers with `depth` steps in flight.
+
+    Three streams: uploads, kernels, downloads.  The upload of step s+1 and the download of step s-1
+    overlap the kernels of step s, but the kernels of different steps never interleave: they all run on
+    ONE stream (a step's library calls are captured once per slot in a CUDA graph and replayed).  With
+    two whole-step graphs on two streams (SequenceTracker x 2) the kernels of neighbouring steps did
+    overlap, and how they happened to interleave moved the end-to-end rate between 403k and 439k
+    pairs/s; a persistent one-CTA-per-SM kernel such as K2s wants the machine to itself.
+
+    submit() is asynchronous and returns the slot; result(slot) waits for that slot's download and
+    returns its pinned output dict (valid until the slot is submitted again)."""
+
+    def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
+                 depth: int = 2, device=None, use_graph: bool = True):
+        torch = _capi.require_cuda()
+        if not cfg.max_matches:
+            raise ValueError("SequencePipeline needs max_matches (compact output stride)")
+        self.torch, self.cfg = torch, cfg
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.F, self.N, self.n_pairs = n_frames, frame_rows, n_frames - 1
+        self.depth = max(1, depth)
+        self.fe = Frontend(cfg, variant=variant)        # kernels are serialised on one stream: one workspace serves every slot
+        self.s_up, self.s_compute, self.s_down = (torch.cuda.Stream(self.dev) for _ in range(3))
+        P, S = self.n_pairs, cfg.max_matches
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "desc": torch.empty((n_frames * frame_rows, DESC_BYTES), dtype=torch.uint8, device=self.dev),
+                "kp": torch.empty((n_frames * frame_rows, 2), dtype=torch.float32, device=self.dev),
+                "out": {"count": pin(P, torch.int32), "best_h": pin(P, torch.int32), "best_count": pin(P, torch.int32),
+                        "out_q": pin(P * S, torch.int32), "out_t": pin(P * S, torch.int32),
+                        "out_d": pin(P * S, torch.int32), "mask": pin(P * S, torch.uint8)},
+                "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event(),
+                "used": False, "batch": None, "graph": None, "res": None})
+        self.h2d_bytes = int(self.F * frame_rows * (DESC_BYTES + 8))
+        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.slots[0]["out"].values()))
+        self.use_graph = use_graph
+        self._counts = None
+        self._next = 0
+
+    def _prepare(self, counts: np.ndarray):
+        """(Re)build the per-slot batches and graphs for this frame-size vector."""
+        torch = self.torch
+        self._counts = np.array(counts, copy=True)
+        torch.cuda.synchronize()
+        for sl in self.slots:
+            sl["batch"] = sequence_batch(sl["desc"], sl["kp"], self._counts, 0, self.n_pairs, self.N)
+            sl["graph"], sl["used"] = None, False
+            with torch.cuda.stream(self.s_compute):
+                sl["res"] = self.fe.run(sl["batch"])                      # eager once: lazy init, workspace
+            self.s_compute.synchronize()
+            if self.use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.s_compute):
+                    sl["res"] = self.fe.run(sl["batch"])
+                sl["graph"] = g
+        torch.cuda.synchronize()
+
+    def submit(self, desc_host, kp_host, counts: np.ndarray, after_compute=None) -> int:
+        """desc_host: pinned uint8 [F*N, 32]; kp_host: pinned float32 [F*N, 2]; counts: rows used per frame."""
+        torch = self.torch
+        if self._counts is None or not np.array_equal(self._counts, counts):
+            self._prepare(counts)
+        i = self._next % self.depth
+        self._next += 1
+        sl = self.slots[i]
+        if sl["used"]:
+            self.s_up.wait_event(sl["computed"])            # the slot's device inputs are free again
+        with torch.cuda.stream(self.s_up):
+            sl["desc"].copy_(desc_host, non_blocking=True)
+            sl["kp"].copy_(kp_host, non_blocking=True)
+            sl["uploaded"].record(self.s_up)
+        self.s_compute.wait_event(sl["uploaded"])
+        if sl["used"]:
+            self.s_compute.wait_event(sl["downloaded"])     # the slot's device results have been read
+        with torch.cuda.stream(self.s_compute):
+            if sl["graph"] is not None:
+                sl["graph"].replay()
+            else:
+                sl["res"] = self.fe.run(sl["batch"])
+            if after_compute is not None:
+                after_compute(sl["res"])
+            sl["computed"].record(self.s_compute)
+        self.s_down.wait_event(sl["computed"])
+        with torch.cuda.stream(self.s_down):
+            res, o = sl["res"], sl["out"]
+            o["count"].copy_(res.sel.count, non_blocking=True)
+            o["best_h"].copy_(res.best_h, non_blocking=True)
+            o["best_count"].copy_(res.best_count, non_blocking=True)
+            o["out_q"].copy_(res.sel.out_q, non_blocking=True)
+            o["out_t"].copy_(res.sel.out_t, non_blocking=True)
+            o["out_d"].copy_(res.sel.out_d, non_blocking=True)
+            o["mask"].copy_(res.inlier_mask, non_blocking=True)
+            sl["downloaded"].record(self.s_down)
+        sl["used"] = True
+        return i
+
+    def result(self, slot: int):
+        self.slots[slot]["downloaded"].synchronize()
+        return self.slots[slot]["out"]
+
+    def streams(self):
+        return (self.s_up, self.s_compute, self.s_down)
 
 
 def pipe_microbench(which: str, iters: int = 2000, ctas_per_sm: int = 8, repeats: int = 5):

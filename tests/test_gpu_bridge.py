@@ -169,3 +169,47 @@ def test_frontend_with_pose_recovers_the_planted_motion():
         Ro, to = ro.decompose_essential(res.E_refit[p].cpu().numpy().reshape(3, 3), corr[sl][inl][:, :2], corr[sl][inl][:, 2:], np.eye(3))
         np.testing.assert_allclose(R[p], Ro, atol=1e-8)
         np.testing.assert_allclose(t[p], to, atol=1e-8)
+
+
+def test_sequence_pipeline_equals_single_shot_frontend():
+    """SequencePipeline (three streams, depth 2, a CUDA graph per buffer set) returns, for every submitted
+    sequence, exactly what one Frontend.run on the same frames returns — also when the slots are reused
+    with different data, and eagerly (use_graph=False)."""
+    import torch
+    from b200slam.frontend import Frontend, FrontendConfig, SequencePipeline, sequence_batch
+    from b200slam.synthetic import tracking_sequence
+    F, N, S = 6, 700, 300
+    cfg = FrontendConfig(hypotheses=256, max_matches=S)
+    counts = np.array([700, 650, 700, 1, 700, 699], np.int32)
+    seqs = [tracking_sequence(F, N, seed=s) for s in (11, 12, 13)]
+    ref = []
+    fe = Frontend(cfg)
+    for desc, kp in seqs:
+        b = sequence_batch(torch.from_numpy(desc.reshape(-1, 32)).cuda(), torch.from_numpy(kp.reshape(-1, 2)).cuda(), counts, 0, F - 1, N)
+        r = fe.run(b)
+        torch.cuda.synchronize()
+        ref.append({k: v.cpu().numpy().copy() for k, v in (("count", r.sel.count), ("best_h", r.best_h), ("best_count", r.best_count),
+                                                           ("out_q", r.sel.out_q), ("out_t", r.sel.out_t), ("out_d", r.sel.out_d),
+                                                           ("mask", r.inlier_mask))})
+    hosts = [(torch.from_numpy(d.reshape(-1, 32)).pin_memory(), torch.from_numpy(k.reshape(-1, 2)).pin_memory()) for d, k in seqs]
+    for use_graph in (True, False):
+        pipe = SequencePipeline(F, N, cfg, depth=2, use_graph=use_graph)
+        order = [0, 1, 2, 1, 0, 2, 2]
+        slots = []
+        for i in order:                                       # submit everything first: slots are reused while in flight
+            slots.append(pipe.submit(hosts[i][0], hosts[i][1], counts))
+            if len(slots) >= 2:                               # read the result of the step before the one just submitted
+                j = len(slots) - 2
+                out = pipe.result(slots[j])
+                for k, v in ref[order[j]].items():
+                    n = len(v)
+                    got = out[k].numpy()[:n]
+                    if k in ("out_q", "out_t", "out_d", "mask"):   # only the first count[p] entries of a pair's stride are defined
+                        for p in range(F - 1):
+                            c = int(ref[order[j]]["count"][p])
+                            assert np.array_equal(got[p * S:p * S + c], v[p * S:p * S + c]), (use_graph, j, k, p)
+                    else:
+                        assert np.array_equal(got, v), (use_graph, j, k)
+        out = pipe.result(slots[-1])
+        assert np.array_equal(out["best_h"].numpy(), ref[order[-1]]["best_h"])
+        torch.cuda.synchronize()
