@@ -409,7 +409,7 @@ def b200_main(a):
                       "ms": t_stage * 1e3, "frac": i8_ops / t_stage / i8_peak},
             "peak_source": "b2s_mma_microbench measured in this run (dense tcgen05.mma kind::i8 M128.N128.K32 from shared memory); "
                            "2 x MEASURED_PEAKS bf16 would be %.0f TOP/s" % (2.0 * bf16_peak),
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_final3_ncu.md",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_final5_ncu.md",
             "note": "algorithmic = ONE 2*256*Nq*Nt int8 contraction per frame pair (SURVEY 8d); the kernel issues 9 K-steps per 8 of "
                     "data (the 9th adds the row/column index), and the two-product variant i8 issues the contraction twice",
             "hamming_variants_ms": variants_ms,
