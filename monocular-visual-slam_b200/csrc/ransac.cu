@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 //   (all to first order in u; the float64 kernel's own rounding is 9 orders of magnitude below).
 //   B below takes 7u, 9u and 10u for the 5u, 6u and 7u (1.4x), and every norm is nudged up by 1e-4.
 constexpr int kScoreHThreads = 128;
-constexpr int kScoreHChunk = 256;   // 4 KB of shared memory: small enough to co-reside with the 220 KB K2s CTA of another stream
+constexpr int kScoreHChunk = 512;   // 8 KB of shared memory: the usual pair (<= 500 correspondences) is staged once, in the pass that also finds W1 / W2
 
 __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
@@ -116,8 +116,14 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     float w1 = 0.0f, w2 = 0.0f;
     for (int m = threadIdx.x; m < M; m += kScoreHThreads) {
       const float4 c = __ldg(cp + m);
+      if (m < kScoreHChunk) s_p[m] = c;   // the first chunk is staged by the same pass
       w1 = fmaxf(w1, fmaf(c.x, c.x, fmaf(c.y, c.y, 1.0f)));
       w2 = fmaxf(w2, fmaf(c.z, c.z, fmaf(c.w, c.w, 1.0f)));
+    }
+    {  // NaN padding of the first chunk's last group (see the chunk loop)
+      const int n0 = min(kScoreHChunk, M), n0_32 = (n0 + 31) & ~31;
+      const float qn = __int_as_float(0x7FC00000);
+      for (int m = n0 + threadIdx.x; m < n0_32; m += kScoreHThreads) s_p[m] = make_float4(qn, qn, qn, qn);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -160,11 +166,13 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   for (int base = 0; base < M; base += kScoreHChunk) {
     const int n = min(kScoreHChunk, M - base);
     const int n32 = (n + 31) & ~31;
-    __syncthreads();
-    // the tail of the last group is padded with NaN: never a certain inlier, and its bits are masked off
-    for (int m = threadIdx.x; m < n32; m += kScoreHThreads)
-      s_p[m] = m < n ? __ldg(cp + base + m) : make_float4(qnan, qnan, qnan, qnan);
-    __syncthreads();
+    if (base > 0) {   // chunk 0 was staged by the prologue (its barrier is the one after the W1 / W2 reduction)
+      __syncthreads();
+      // the tail of the last group is padded with NaN: never a certain inlier, and its bits are masked off
+      for (int m = threadIdx.x; m < n32; m += kScoreHThreads)
+        s_p[m] = m < n ? __ldg(cp + base + m) : make_float4(qnan, qnan, qnan, qnan);
+      __syncthreads();
+    }
     for (int m0 = 0; m0 < n32; m0 += 32) {
       uint32_t band = 0u;
 #pragma unroll
