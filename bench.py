@@ -49,7 +49,7 @@ def parse():
                     help="Hamming kernel: K1 POPC, K2 tcgen05 kind::i8 with two products, K2s single product (shipped default)")
     ap.add_argument("--chunks", type=int, default=1, help="e2e: copy/compute overlap chunks")
     ap.add_argument("--scoring", default="cuda", choices=["tc", "cuda"], help="RANSAC scoring: K3t tensor cores or K3h CUDA cores (same counts)")
-    ap.add_argument("--e2e-depth", type=int, default=2, help="e2e: steps in flight (device/pinned buffer sets)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: steps in flight (device/pinned buffer sets)")
     ap.add_argument("--e2e-mode", default="graphs", choices=["single", "graphs"],
                     help="e2e: 'graphs' = one whole-step graph per tracker and stream (default, 437k pairs/s); "
                          "'single' = SequencePipeline, one kernel stream with overlapping copies (427k, interleave-proof)")
