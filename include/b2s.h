@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B2S_ABI_VERSION 1
+#define B2S_ABI_VERSION 2
 #define B2S_IDX_BITS 22
 #define B2S_IDX_MASK ((1u << B2S_IDX_BITS) - 1u)
 #define B2S_NONE_KEY 0xFFFFFFFFu
@@ -70,9 +70,12 @@ int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz)
  * train axis (0 = choose automatically); workspace must hold
  * b2s_hamming_workspace_bytes(total_nq, t_split_max) bytes when t_split != 1. */
 size_t b2s_hamming_workspace_bytes(int total_nq, int t_split);
-/* Workspace of either variant.  The I8MMA variant stages every descriptor as 256 int8
- * (+1/-1) in 40 KB operand tiles: n_pairs * (ceil(max_nq/128) + ceil(max_nt/128)) * 40 KB,
- * 128-byte aligned; t_split is ignored by it. */
+/* Workspace of either variant.  The I8MMA variants stage every descriptor as 256 int8 (+8/-8)
+ * in 36 KB operand tiles (128 rows x 18 k-chunks of 16 B): n_pairs * (ceil(max_nq/128) +
+ * ceil(max_nt/128)) * 36 KB, 128-byte aligned.  The single-product variant (I8MMA1) also honours
+ * t_split (0 = automatic: a batch with fewer (pair, query block) work items than SMs — one
+ * 10 000 x 10 000 pair, a lone 2000 x 2000 drop-in call — is cut along the train axis and the
+ * partial top-2 merged on the packed keys) and adds total_nq * t_split * 8 bytes for it. */
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt,
                                      int t_split);
 int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc,
@@ -103,14 +106,16 @@ int b2s_hamming_get_config(int* csa_level, int* rows_per_thread, int* warps);
  *              not the CSR offset (shared frames, as q_src_row/t_src_row above).
  *   out_stride: 0 -> pair p's outputs live at [q_off[p], q_off[p] + out_count[p]);
  *              > 0 -> at [p*out_stride, p*out_stride + out_count[p]) (compact layout for
- *              truncated selections; a pair that does not fit gets out_count = -1). */
+ *              truncated selections; a pair that does not fit gets out_count = -1).
+ *   out_total: optional (n_pairs int32): matches that passed the tests BEFORE truncation to max_matches
+ *              (the relocalization sweep ranks keyframes by it). */
 int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_second,
                        const uint32_t* bwd_best, const int32_t* q_off, const int32_t* t_off,
                        int n_pairs, int max_nq, int use_ratio, int use_cross,
                        const int32_t* ratio_lut_host, int sort_by_distance, int max_matches,
                        const float* kp_q, const float* kp_t, const int32_t* kp_q_src_row,
                        const int32_t* kp_t_src_row, int out_stride, int32_t* out_q, int32_t* out_t,
-                       int32_t* out_d, float* out_corr, int32_t* out_count, void* stream);
+                       int32_t* out_d, float* out_corr, int32_t* out_count, int32_t* out_total, void* stream);
 
 /* ---- K4: batched 8-point minimal solver ---------------------------------------
  * Replaces the per-iteration body of ransac_essential up to the hypothesis
@@ -118,14 +123,16 @@ int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_second,
  * corr: float32 (x1,y1,x2,y2) per correspondence; pair p owns
  * [c_off[p], c_off[p]+c_count[p]).  For every pair, H hypotheses:
  *   samples_in != NULL: use samples_in[(p*H+h)*8 .. +7] (seeded host draws, parity mode)
- *   samples_in == NULL: draw 8 distinct indices on device from (seed, p, h)
+ *   samples_in == NULL: draw 8 distinct indices on device from (seed, id(p), h), id(p) = pair_ids[p]
+ *                       (device int32, optional) or pair_id0 + p: the pair's GLOBAL id, so that a pair
+ *                       draws the same samples on whichever rank / batch position it is processed
  * samples_out (optional) receives the indices used.  K_host / Kinv_host: HOST
  * pointers to 9 doubles, row-major (NULL = identity).  E_out: (n_pairs*H*9) doubles.
  * Pairs with fewer than 8 correspondences get all-zero hypotheses. */
 int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32_t* c_count,
                             int n_pairs, int H, const int32_t* samples_in, uint64_t seed,
-                            int32_t* samples_out, const double* K_host, const double* Kinv_host,
-                            double* E_out, void* stream);
+                            const int32_t* pair_ids, int pair_id0, int32_t* samples_out,
+                            const double* K_host, const double* Kinv_host, double* E_out, void* stream);
 
 /* ---- K3: batched Sampson-error hypothesis scoring ------------------------------
  * Replaces homography.py:328-333 for all hypotheses at once.
@@ -134,10 +141,13 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
  * precision: 64 = float64 decisions (float32 screening with a rigorous rounding bound, the
  * undecidable band re-evaluated in float64 — counts identical to 6464 at ~0.6x the time),
  * 6464 = every evaluation in float64 (the reference's arithmetic, kept for validation),
- * 32 = float32 only (within the north-star flip tolerance, not bit-identical). */
+ * 32 = float32 only (within the north-star flip tolerance, not bit-identical).
+ * max_m: host-known upper bound of any c_count[p], or 0 = unknown; with precision 64 a batch of few
+ * pairs with thousands of correspondences each is then also cut along the correspondences (partial
+ * counts summed with atomicAdd) so that it fills the machine. */
 int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int32_t* c_count,
                              int n_pairs, const double* E, int H, double th2,
-                             const double* th2_per_pair, int precision, int32_t* counts,
+                             const double* th2_per_pair, int precision, int max_m, int32_t* counts,
                              void* stream);
 
 /* K5 / K6 — batched RANSAC homography (next-row #3).  Same conventions as the essential-matrix
@@ -200,14 +210,19 @@ int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_
  * tiles start at tile blk_tile0[b] (prefix sum of ceil(rows / 128); total_tiles in all);
  * q_xtile[p] / t_xtile[p] = first tile of pair p's query / train block; q_off / t_off = CSR of the
  * OUTPUT rows (q_off[p+1] - q_off[p] must equal the query block's rows).  All index arrays int32 on
- * the device.  Outputs as b2s_hamming_knn2_batched.  workspace: b2s_hamming_shared_workspace_bytes. */
-size_t b2s_hamming_shared_workspace_bytes(int total_tiles);
+ * the device.  Outputs and t_split as b2s_hamming_knn2_batched.  workspace: b2s_hamming_shared_workspace_bytes
+ * (same n_pairs / total_nq / max_nq / max_nt / t_split as the call). */
+size_t b2s_hamming_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt,
+                                          int t_split);
 int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
                             const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                             const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                             int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                            uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
-                            void* stream);
+                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Diagnostics: work decomposition of the most recent single-product launch — query sub-tiles per
+ * work item (2 or 4), train-axis split, CTAs. */
+void b2s_hamming_last_plan(int* subs, int* t_split, int* grid);
 
 /* K9 — bag-of-words candidate ranking, the step in front of the relocalizer's matching (next-row #4).
  * b2s_bow_histogram_batched  replaces compute_bow_histogram (persistent_map.py:82-96) and
@@ -249,6 +264,35 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
                       const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
                       uint8_t* inlier_mask, void* stream);
 
+/* ---- result records: what leaves the GPU ------------------------------------------
+ * One fixed-size record per pair, written by ONE kernel straight into the buffer that is all-gathered over
+ * NCCL when pairs are sharded across GPUs or copied to the host in one transfer.  Replaces
+ * the Python result objects of the reference: list[cv2.DMatch] (feature_pipeline.py.bak:78-95) and
+ * (R, t, inliers, match_count) (homography.py:423-438).
+ *   record = int32 header[16] { n_matches, best_h, inlier_count, pair_id, R[9] as float32 bits, t[3] as float32 bits }
+ *            | uint16 queryIdx[S] | uint16 trainIdx[S] | uint16 distance[S] | uint8 inlier[S] | pad to 64 bytes
+ * S = stride = the compact selection stride (max_matches; rows per frame must be < 65536).
+ * count / out_q / out_t / out_d / inlier_mask: the selection and winner outputs (compact layout, pair p at
+ * p * stride); count_total (optional): header n_matches when it differs from the selected count (matches
+ * before truncation); R / t (optional, float64 [.][9] / [.][3]); pair_ids (optional) overrides
+ * pair_id0 + p; src_pair (optional, n_records int32): record r describes pair src_pair[r] (-1 = empty
+ * slot) and best_h / best_count / R / t are then indexed by r (ranked candidates, b2s_rank_pairs). */
+size_t b2s_record_bytes(int max_matches);
+int b2s_pack_records(const int32_t* count, const int32_t* count_total, const int32_t* best_h, const int32_t* best_count,
+                     const int32_t* out_q, const int32_t* out_t, const int32_t* out_d, const uint8_t* inlier_mask,
+                     const double* R, const double* t, const int32_t* pair_ids, const int32_t* src_pair, int n_records,
+                     int stride, int pair_id0, uint8_t* records, size_t record_bytes, void* stream);
+
+/* The k (<= 32) pairs with the largest score, ties to the lower id then the lower position — the candidate
+ * ranking of MapRelocalizer.relocalize (persistent_map.py:236-242: sorted by (-score, frame_id), first
+ * max_candidates) on the device, for the whole-map sweep (BASELINE config #5: score = cross-check match
+ * count).  score < 0 excludes a pair.  top_idx [k] = pair index or -1; top_id [k] (optional) = its id (-1);
+ * c_off / c_count (optional, [k]) =
+ * CSR view of the winners' compact correspondences (top_idx * stride, sel_count[top_idx]) for the RANSAC
+ * entry points. */
+int b2s_rank_pairs(const int32_t* score, const int32_t* ids, const int32_t* sel_count, int n, int k, int stride,
+                   int32_t* top_idx, int32_t* top_id, int32_t* c_off, int32_t* c_count, void* stream);
+
 /* ---- measurement helper ----------------------------------------------------------
  * Saturates one SM pipe with independent instructions to measure its rate:
  * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD, 7 REDUX.MIN, 8 SHFL.
@@ -262,7 +306,8 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
  * [2] MMA waiting for operand tiles, [3] producer waiting for a free ring slot, [4] epilogue
  * warp total, [5] epilogue waiting for accumulators, [6] tile pairs.  NULL switches it off.
  * mode (results become meaningless, timing only): bit 0 = the epilogue drains nothing,
- * bit 1 = the operand ring is loaded once and then reused.  0 = normal operation. */
+ * bit 1 = the operand ring is loaded once and then reused.  Bits that keep the results exact:
+ * 16 = the 32x32b A/B epilogue, 32 / 64 = force 2 / 4 query sub-tiles per work item.  0 = normal. */
 void b2s_hamming_i8_debug(unsigned long long* dev_buf, int mode);
 
 /* Measurement: enable = 1 / 0 switches a CUDA-event pair around the tcgen05 Hamming kernel

@@ -107,7 +107,7 @@ def ransac_essential_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000,
     th = np.broadcast_to(np.asarray(th, np.float64), (n_pairs,))
     th2_d = torch.from_numpy(np.ascontiguousarray(th ** 2)).to(dev)
     E = R.hypotheses(corr_d, off_d, cnt_d, n_pairs, max_iter, samples=samples_d, seed=seed, K=K)
-    counts = R.score(corr_d, off_d, cnt_d, n_pairs, E, 0.0, th2_per_pair=th2_d, precision=64)
+    counts = R.score(corr_d, off_d, cnt_d, n_pairs, E, 0.0, th2_per_pair=th2_d, precision=64, max_m=int(counts_np.max()) if n_pairs else 0)
     best_h, best_c, mask = R.select(counts, corr_d, off_d, cnt_d, n_pairs, E, 0.0, th2_per_pair=th2_d)
     best_h, mask = best_h.cpu().numpy(), mask.cpu().numpy()
     return [(int(best_h[p]), np.flatnonzero(mask[off[p]:off[p + 1]])) for p in range(n_pairs)]
@@ -484,20 +484,26 @@ class RobustPoseEstimator:
 
 def install() -> list[str]:
     """Rebind the hot-path names in whichever reference modules are importable
-    (``homography``, ``robust_pose_estimator``, ``persistent_map``, ``slam_api``,
-    ``keyframe_manager``).  Returns the list of ``module.name`` strings patched."""
+    (``homography``, ``robust_pose_estimator``, ``persistent_map``, ``keyframe_manager``, ``slam_api``,
+    ``visual_slam_offline_entry_point``).  Modules that did ``from x import name`` keep their own
+    reference to the old object, so every importer is patched by name as well — the result does not
+    depend on import order.  Returns the list of ``module.name`` strings patched; names that were looked
+    for but could not be patched (module not importable, attribute absent) are in ``install.skipped``."""
     import importlib
 
-    patched = []
+    patched, skipped = [], []
 
     def bind(modname, attr, obj):
         try:
             mod = importlib.import_module(modname)
         except Exception:                                    # module absent or its own deps missing
+            skipped.append(f"{modname}.{attr}")
             return
         if hasattr(mod, attr):
             setattr(mod, attr, obj)
             patched.append(f"{modname}.{attr}")
+        else:
+            skipped.append(f"{modname}.{attr}")
 
     for name, obj in (("ransac_essential", ransac_essential), ("estimate_pose_from_matches", estimate_pose_from_matches),
                       ("match_orb_descriptors", match_orb_descriptors), ("ransac_homography", ransac_homography),
@@ -519,7 +525,36 @@ def install() -> list[str]:
 
         relocalization_bridge.RelocalizationResult = persistent_map.RelocalizationResult
         bind("persistent_map", "MapRelocalizer", relocalization_bridge.BatchedMapRelocalizer)
+        bind("slam_api", "MapRelocalizer", relocalization_bridge.BatchedMapRelocalizer)          # slam_api.py:43 binds it by name
+        bind("relocalization_demo", "MapRelocalizer", relocalization_bridge.BatchedMapRelocalizer)
         bind("persistent_map", "compute_bow_histogram", relocalization_bridge.compute_bow_histogram)   # K9 (build_snapshot, :110-112)
     except Exception:
-        pass
+        skipped.append("persistent_map.MapRelocalizer")
+    try:                                                    # keyframe overlap (keyframe_manager.py:123-155): the reference builds a
+        import keyframe_manager                             # cv2.BFMatcher per call unless a matcher= callable was injected
+
+        base = keyframe_manager.KeyframeManager
+        if getattr(base, "_b2s_device_matcher", False):     # install() twice: keep the class of the first call
+            KeyframeManager = base
+        else:
+            class KeyframeManager(base):                    # same constructor; matcher=None now means the device cross-check matcher
+                _b2s_device_matcher = True
+
+                def __init__(self, *args, **kwargs):
+                    super().__init__(*args, **kwargs)
+                    if self.matcher is None:
+                        self.matcher = CrossCheckMatcher().match
+
+            KeyframeManager.__qualname__ = base.__qualname__
+            KeyframeManager.__module__ = base.__module__
+        for mod in ("keyframe_manager", "slam_api", "visual_slam_offline_entry_point"):
+            bind(mod, "KeyframeManager", KeyframeManager)
+    except Exception:
+        skipped.append("keyframe_manager.KeyframeManager")
+    install.skipped = skipped
+    if skipped:
+        LOGGER.debug("install(): not patched: %s", ", ".join(skipped))
     return patched
+
+
+install.skipped = []

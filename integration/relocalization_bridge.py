@@ -207,6 +207,7 @@ class BatchedMapRelocalizer:
         self._bow_scorer = bow_scorer
         self._map_dev = None
         self._bow_dev = None
+        self._map_hists_dev = None
 
     # ---- persistent_map.py:226-319 ----------------------------------------------------------
     def relocalize(self, keypoints, descriptors: np.ndarray):
@@ -283,13 +284,15 @@ class BatchedMapRelocalizer:
         if not _is_orb(descriptors, vocab):
             return host_bow_scores(descriptors, vocab, hists)
         if self._bow_dev is None:
+            # the vocabulary object is shared process-wide (keyed by its bytes); THIS map's histograms stay
+            # with this relocalizer, so two relocalizers over different snapshots never see each other's map
             self._bow_dev = _bow_index(vocab)
-            self._bow_dev.set_map(hists)
+            self._map_hists_dev = self._bow_dev.upload_map(hists)
         import torch
         idx = self._bow_dev
         d = torch.from_numpy(np.ascontiguousarray(descriptors)).to(idx.dev)
         off = torch.tensor([0, len(descriptors)], dtype=torch.int32, device=idx.dev)
-        return idx.scores(idx.histograms(d, off, 1, len(descriptors))[0]).cpu().numpy()
+        return idx.scores(idx.histograms(d, off, 1, len(descriptors))[0], self._map_hists_dev).cpu().numpy()
 
     def _solve_poses(self, pairs):
         """estimate_pose_from_matches (homography.py:423-438) for every surviving candidate:

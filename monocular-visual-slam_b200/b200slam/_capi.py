@@ -21,6 +21,7 @@ IDX_MASK = (1 << IDX_BITS) - 1
 NONE_KEY = 0xFFFFFFFF
 DESC_BYTES = 32
 SELECT_MAX_QUERIES = 32768
+ABI_VERSION = 2
 VARIANT_POPC = 0
 VARIANT_I8MMA = 1
 VARIANT_I8MMA1 = 2
@@ -58,20 +59,28 @@ def _declare(lib):
     lib.b2s_hamming_knn2_batched.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                              vp, vp, vp, i32, i32, vp, sz, vp]
     lib.b2s_hamming_shared_workspace_bytes.restype = sz
-    lib.b2s_hamming_shared_workspace_bytes.argtypes = [i32]
+    lib.b2s_hamming_shared_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+    lib.b2s_hamming_last_plan.restype = None
+    lib.b2s_hamming_last_plan.argtypes = [ip, ip, ip]
     lib.b2s_hamming_knn2_shared.restype = i32
-    lib.b2s_hamming_knn2_shared.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.b2s_hamming_knn2_shared.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, sz, vp]
     lib.b2s_hamming_set_config.restype = i32
     lib.b2s_hamming_set_config.argtypes = [i32, i32, i32]
     lib.b2s_hamming_get_config.restype = i32
     lib.b2s_hamming_get_config.argtypes = [ip, ip, ip]
     lib.b2s_select_matches.restype = i32
     lib.b2s_select_matches.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32,
-                                       vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+                                       vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.b2s_record_bytes.restype = sz
+    lib.b2s_record_bytes.argtypes = [i32]
+    lib.b2s_pack_records.restype = i32
+    lib.b2s_pack_records.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.b2s_rank_pairs.restype = i32
+    lib.b2s_rank_pairs.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.b2s_eight_point_batched.restype = i32
-    lib.b2s_eight_point_batched.argtypes = [vp, vp, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]
+    lib.b2s_eight_point_batched.argtypes = [vp, vp, vp, i32, i32, vp, u64, vp, i32, vp, vp, vp, vp, vp]
     lib.b2s_ransac_score_batched.restype = i32
-    lib.b2s_ransac_score_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, i32, vp, vp]
+    lib.b2s_ransac_score_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, i32, i32, vp, vp]
     lib.b2s_ransac_score_tc_workspace_bytes.restype = sz
     lib.b2s_ransac_score_tc_workspace_bytes.argtypes = [i32, i32, i32]
     lib.b2s_ransac_score_tc.restype = i32
@@ -116,7 +125,8 @@ EXPORTS = (
     "b2s_ransac_select", "b2s_pipe_microbench", "b2s_mma_microbench", "b2s_tmem_microbench",
     "b2s_hamming_i8_debug", "b2s_hamming_kernel_timing", "b2s_ransac_score_tc_workspace_bytes", "b2s_ransac_score_tc",
     "b2s_homography_dlt_batched", "b2s_homography_score_batched", "b2s_homography_select", "b2s_decompose_essential_batched", "b2s_refit_essential_batched", "b2s_pose_pick", "b2s_five_point_batched",
-    "b2s_bow_histogram_batched", "b2s_bow_cosine", "b2s_hamming_shared_workspace_bytes", "b2s_hamming_knn2_shared",
+    "b2s_bow_histogram_batched", "b2s_bow_cosine", "b2s_hamming_shared_workspace_bytes", "b2s_hamming_knn2_shared", "b2s_hamming_last_plan",
+    "b2s_record_bytes", "b2s_pack_records", "b2s_rank_pairs",
 )
 
 
@@ -133,7 +143,7 @@ def load_library():
                 "or `make -C monocular-visual-slam_b200/csrc`. There is no CPU fallback.")
         _lib = _declare(C.CDLL(str(path)))
         _lib_pid = os.getpid()
-        if _lib.b2s_abi_version() != 1:
+        if _lib.b2s_abi_version() != ABI_VERSION:
             raise B2SError("libb2s.so ABI version mismatch")
         return _lib
 

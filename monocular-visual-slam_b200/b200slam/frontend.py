@@ -186,6 +186,7 @@ class Selection:
     corr: "torch.Tensor | None"
     c_off: "torch.Tensor"
     stride: int = 0
+    total: "torch.Tensor | None" = None    # matches per pair before truncation to max_matches (with_total=True)
 
 
 class HammingMatcher:
@@ -210,17 +211,20 @@ class HammingMatcher:
         sh = b.shared
         if sh is not None and self.variant == _capi.VARIANT_I8MMA1 and nq > 0 and nt > 0 and b.q_desc.data_ptr() == b.t_desc.data_ptr():
             # pairs share descriptor blocks (frames): every block is expanded once
-            ws_bytes = int(self._lib.b2s_hamming_shared_workspace_bytes(sh.total_tiles))
+            ws_bytes = int(self._lib.b2s_hamming_shared_workspace_bytes(sh.total_tiles, b.n_pairs, nq, b.max_nq, b.max_nt, self.t_split))
             if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
                 self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             check(self._lib.b2s_hamming_knn2_shared(
                 ptr(b.q_desc), ptr(sh.row0), ptr(sh.rows), ptr(sh.tile0), sh.n_blocks, sh.total_tiles, sh.max_rows,
                 ptr(sh.q_xtile), ptr(sh.t_xtile), ptr(b.q_off), ptr(b.t_off), b.n_pairs, nq, nt, b.max_nq, b.max_nt,
-                ptr(fb), ptr(fs), ptr(bb), self._ws.data_ptr(), ws_bytes, current_stream()))
+                ptr(fb), ptr(fs), ptr(bb), self.t_split, self._ws.data_ptr(), ws_bytes, current_stream()))
             return Keys(fb[:nq], fs[:nq], bb[:nt])
         if nq > 0 and (self.variant != _capi.VARIANT_POPC or self.t_split != 1):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            want = self.t_split if self.t_split > 1 else max(1, min(64, (4 * sms) // max(1, b.n_pairs)))
+            if self.variant == _capi.VARIANT_POPC:
+                want = self.t_split if self.t_split > 1 else max(1, min(64, (4 * sms) // max(1, b.n_pairs)))
+            else:
+                want = self.t_split          # tensor-core kernels: 0 = the library's own plan
             ws_bytes = int(self._lib.b2s_hamming_workspace_bytes_v(self.variant, b.n_pairs, nq, b.max_nq, b.max_nt, want))
             if ws_bytes:
                 if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
@@ -234,7 +238,7 @@ class HammingMatcher:
 
     def select(self, b: PairBatch, k: Keys, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
                sort_by_distance: bool = True, max_matches: int | None = None,
-               with_corr: bool = False, compact: bool = False) -> Selection:
+               with_corr: bool = False, compact: bool = False, with_total: bool = False) -> Selection:
         torch = _capi.require_cuda()
         dev = b.q_desc.device
         nq = b.total_nq
@@ -244,6 +248,7 @@ class HammingMatcher:
         ot = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
         od = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
         cnt = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev)
+        total = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev) if with_total else None
         corr = None
         if with_corr:
             if b.kp_q is None or b.kp_t is None:
@@ -262,9 +267,9 @@ class HammingMatcher:
             b.n_pairs, b.max_nq, int(use_ratio), int(use_cross), ptr(lut), int(sort_by_distance),
             int(max_matches or 0), ptr(b.kp_q) if with_corr else None, ptr(b.kp_t) if with_corr else None,
             ptr(b.q_src) if with_corr else None, ptr(b.t_src) if with_corr else None, stride,
-            ptr(oq), ptr(ot), ptr(od), ptr(corr), ptr(cnt), current_stream()))
+            ptr(oq), ptr(ot), ptr(od), ptr(corr), ptr(cnt), ptr(total), current_stream()))
         return Selection(oq[:rows], ot[:rows], od[:rows], cnt[:b.n_pairs], None if corr is None else corr[:rows],
-                         c_off, stride)
+                         c_off, stride, None if total is None else total[:b.n_pairs])
 
     # ---- host convenience: numpy in, numpy out (includes H2D / D2H) -------------------
     def match_pairs(self, q_list, t_list, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
@@ -317,14 +322,16 @@ class EssentialRansac:
         return Kd, Kinv, (Kd, Kinv)
 
     def hypotheses(self, corr, c_off, c_count, n_pairs: int, H: int, *, samples=None, seed: int = 0,
-                   K=None, return_samples: bool = False):
+                   K=None, return_samples: bool = False, pair_ids=None, pair_id0: int = 0):
+        """pair_ids (device int32 [n_pairs]) / pair_id0: the pairs' GLOBAL ids; the device sample stream is keyed
+        by (seed, id, h), so sharded and single-GPU runs draw the same samples for the same pair."""
         torch = _capi.require_cuda()
         E = torch.empty((max(n_pairs, 1), max(H, 1), 9), dtype=torch.float64, device=corr.device)
         s_out = torch.empty((max(n_pairs, 1), max(H, 1), 8), dtype=torch.int32, device=corr.device) if return_samples else None
         Kd, Kinv, _keep = self._k_args(K)
         check(self._lib.b2s_eight_point_batched(
             ptr(corr), ptr(c_off), ptr(c_count), n_pairs, H, ptr(samples), C.c_uint64(seed & (2**64 - 1)),
-            ptr(s_out), ptr(Kd), ptr(Kinv), ptr(E), current_stream()))
+            ptr(pair_ids), int(pair_id0), ptr(s_out), ptr(Kd), ptr(Kinv), ptr(E), current_stream()))
         E = E[:n_pairs, :H]
         return (E, s_out[:n_pairs, :H]) if return_samples else E
 
@@ -361,13 +368,15 @@ class EssentialRansac:
         counts = counts[:n_pairs, :H]
         return (counts, num, den, band) if debug else counts
 
-    def score(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, precision: int = 64):
+    def score(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, precision: int = 64, max_m: int = 0):
+        """max_m: host-known bound on the correspondences of a pair (0 = unknown); lets a batch of few
+        pairs with thousands of correspondences each (BASELINE config #4) be cut along the correspondences too."""
         torch = _capi.require_cuda()
         H = E.shape[1]
         counts = torch.empty((max(n_pairs, 1), max(H, 1)), dtype=torch.int32, device=corr.device)
         check(self._lib.b2s_ransac_score_batched(
             ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2), ptr(th2_per_pair),
-            precision, ptr(counts), current_stream()))
+            precision, int(max_m), ptr(counts), current_stream()))
         return counts[:n_pairs, :H]
 
     def select(self, counts, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None):
@@ -380,6 +389,56 @@ class EssentialRansac:
             ptr(counts), ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2),
             ptr(th2_per_pair), ptr(best_h), ptr(best_c), ptr(mask), current_stream()))
         return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
+
+
+# ---- result records (csrc/records.cu): ONE fixed-size record per pair is what leaves the GPU ------------
+RECORD_HEADER_BYTES = 64
+
+
+def record_bytes(max_matches: int) -> int:
+    return int(_capi.load_library().b2s_record_bytes(int(max_matches)))
+
+
+def pack_records(records, sel: Selection, best_h=None, best_count=None, mask=None, R=None, t=None, *, n_records: int,
+                 pair_id0: int = 0, pair_ids=None, src_pair=None, count_total=None):
+    """Write one record per pair into `records` (device uint8 [n_records, record_bytes(sel.stride)], e.g. this
+    rank's slice of the all-gather buffer) on the current stream: header (n_matches, best_h, inliers, pair id,
+    R | t as float32) + stride x (queryIdx u16, trainIdx u16, distance u16, inlier u8)."""
+    if not sel.stride:
+        raise ValueError("records need the compact selection layout (max_matches / stride)")
+    check(_capi.load_library().b2s_pack_records(
+        ptr(sel.count), ptr(count_total), ptr(best_h), ptr(best_count), ptr(sel.out_q), ptr(sel.out_t), ptr(sel.out_d),
+        ptr(mask), ptr(R), ptr(t), ptr(pair_ids), ptr(src_pair), int(n_records), int(sel.stride), int(pair_id0),
+        records.data_ptr(), int(records.shape[-1]) if records.ndim > 1 else record_bytes(sel.stride), current_stream()))
+    return records
+
+
+def unpack_records(buf, stride: int):
+    """Host view of a record buffer (NumPy uint8 [n, record_bytes]) -> dict of arrays: n_matches, best_h,
+    inliers, pair_id (int32 [n]); R float32 [n, 3, 3]; t float32 [n, 3]; q, t_idx, d (uint16 [n, stride]);
+    inlier (uint8 [n, stride]).  Entries past n_matches are zero."""
+    a = np.ascontiguousarray(np.asarray(buf, dtype=np.uint8))
+    if a.ndim == 1:
+        a = a.reshape(-1, record_bytes(stride))
+    n = a.shape[0]
+    hdr = a[:, :64].copy().view(np.int32).reshape(n, 16)
+    body = a[:, 64:64 + 6 * stride].copy().view(np.uint16).reshape(n, 3, stride)
+    return {"n_matches": hdr[:, 0], "best_h": hdr[:, 1], "inliers": hdr[:, 2], "pair_id": hdr[:, 3],
+            "R": hdr[:, 4:13].copy().view(np.float32).reshape(n, 3, 3), "t": hdr[:, 13:16].copy().view(np.float32).reshape(n, 3),
+            "q": body[:, 0], "t_idx": body[:, 1], "d": body[:, 2], "inlier": a[:, 64 + 6 * stride:64 + 7 * stride]}
+
+
+def rank_pairs(score, k: int, *, ids=None, sel_count=None, stride: int = 0, with_ids: bool = False):
+    """The k (<= 32) pairs with the largest score, ties to the lower id then position, on the device
+    (persistent_map.py:236-242).  -> (top_idx [k], c_off [k], c_count [k]) int32 device tensors."""
+    torch = _capi.require_cuda()
+    dev = score.device
+    out = torch.empty((4, max(k, 1)), dtype=torch.int32, device=dev)
+    check(_capi.load_library().b2s_rank_pairs(ptr(score), ptr(ids), ptr(sel_count), int(score.numel()), int(k), int(stride),
+                                             ptr(out[0]), ptr(out[3]), ptr(out[1]), ptr(out[2]), current_stream()))
+    if with_ids:
+        return out[0, :k], out[1, :k], out[2, :k], out[3, :k]
+    return out[0, :k], out[1, :k], out[2, :k]
 
 
 class PoseRecovery:
@@ -517,28 +576,35 @@ class BowIndex:
             return out[0].cpu().numpy(), out[1].cpu().numpy()[: off[-1]]
         return out.cpu().numpy()
 
-    def set_map(self, hists):
-        """Keep the map's histograms [n, k] resident on the device."""
+    def upload_map(self, hists):
+        """Map histograms [n, k] -> a device float32 tensor the CALLER keeps (one vocabulary object may
+        serve several maps: old and new snapshot, two relocalizers)."""
         import torch
 
         h = hists if hasattr(hists, "data_ptr") else torch.from_numpy(np.ascontiguousarray(hists, dtype=np.float32))
         if h.ndim != 2 or h.shape[1] != self.k:
             raise ValueError("map histograms must be [n, k]")
-        self.map_hists = h.to(self.dev, dtype=torch.float32).contiguous()
+        return h.to(self.dev, dtype=torch.float32).contiguous()
 
-    def scores(self, hist_q):
-        """hist_q: device float32 [k] (or host array) -> device float32 [n] cosine scores against the map."""
+    def set_map(self, hists):
+        """Convenience for a single-map owner of this object: keep the histograms here."""
+        self.map_hists = self.upload_map(hists)
+
+    def scores(self, hist_q, map_hists=None):
+        """hist_q: device float32 [k] (or host array) -> device float32 [n] cosine scores against
+        `map_hists` (device tensor from upload_map; default: the one given to set_map)."""
         import torch
 
-        if self.map_hists is None:
-            raise ValueError("set_map() first")
+        hists = self.map_hists if map_hists is None else map_hists
+        if hists is None:
+            raise ValueError("set_map() first, or pass map_hists")
         q = hist_q if hasattr(hist_q, "data_ptr") else torch.from_numpy(np.ascontiguousarray(hist_q, dtype=np.float32))
         q = q.to(self.dev, dtype=torch.float32).contiguous().reshape(-1)
         if q.numel() != self.k:
             raise ValueError("query histogram must have k entries")
-        n = int(self.map_hists.shape[0])
+        n = int(hists.shape[0])
         out = torch.empty((n,), dtype=torch.float32, device=self.dev)
-        check(self.lib.b2s_bow_cosine(ptr(q), ptr(self.map_hists), n, self.k, ptr(out), current_stream()))
+        check(self.lib.b2s_bow_cosine(ptr(q), ptr(hists), n, self.k, ptr(out), current_stream()))
         return out
 
 
@@ -572,6 +638,7 @@ class FrontendResult:
     R: "torch.Tensor | None" = None
     t: "torch.Tensor | None" = None
     votes: "torch.Tensor | None" = None
+    records: "torch.Tensor | None" = None
 
 
 class Frontend:
@@ -589,16 +656,20 @@ class Frontend:
         th2 = c.threshold ** 2
         if c.scoring == "tc" and c.precision == 64:
             return self.ransac.score_tc(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, max_m=sel.stride or b.max_nq)
-        return self.ransac.score(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, precision=c.precision)
+        return self.ransac.score(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, precision=c.precision,
+                                 max_m=sel.stride or b.max_nq)
 
-    def run(self, b: PairBatch, K=None, samples=None) -> FrontendResult:
+    def run(self, b: PairBatch, K=None, samples=None, records=None, pair_id0: int = 0) -> FrontendResult:
+        """records: optional device uint8 [n_pairs, record_bytes(max_matches)] — e.g. this rank's slice of the
+        all-gather buffer, or the staging buffer of the step's one device->host copy; the last kernel of the
+        step writes every pair's result record into it (pair ids pair_id0 + p)."""
         c = self.cfg
         keys = self.matcher.knn2(b)
         sel = self.matcher.select(b, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
                                   sort_by_distance=True, max_matches=c.max_matches, with_corr=True,
                                   compact=True)
         E = self.ransac.hypotheses(sel.corr, sel.c_off, sel.count, b.n_pairs, c.hypotheses,
-                                   samples=samples, seed=c.seed, K=K)
+                                   samples=samples, seed=c.seed, K=K, pair_id0=pair_id0)
         th2 = c.threshold ** 2
         counts = self.score(sel, b, E)
         best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
@@ -608,22 +679,44 @@ class Frontend:
                 self.pose = PoseRecovery()
             res.E_refit, res.R, res.t, res.votes = self.pose.recover(sel.corr, sel.c_off, sel.count, b.n_pairs,
                                                                       sel.stride or b.max_nq, mask=mask, K=K)
+        if records is not None:
+            pack_records(records, sel, best_h, best_c, mask, res.R, res.t, n_records=b.n_pairs, pair_id0=pair_id0)
+            res.records = records
         return res
 
 
+class RecordView(dict):
+    """The result of a step as the arrays the reference hands back, unpacked lazily from the ONE pinned record
+    buffer the step downloaded: count, best_h, best_count (per pair), out_q / out_t / out_d / mask (compact,
+    stride = max_matches), R [P, 3, 3], t [P, 3] (float32; zero unless the step ran with_pose)."""
+
+    def __init__(self, host_records, stride: int):
+        super().__init__()
+        self.records, self.stride = host_records, stride
+
+    def _fill(self):
+        import torch
+
+        u = unpack_records(self.records.numpy(), self.stride)
+        flat = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1))
+        dict.update(self, {"count": torch.from_numpy(u["n_matches"].copy()), "best_h": torch.from_numpy(u["best_h"].copy()),
+                           "best_count": torch.from_numpy(u["inliers"].copy()), "pair_id": torch.from_numpy(u["pair_id"].copy()),
+                           "out_q": flat(u["q"].astype(np.int32)), "out_t": flat(u["t_idx"].astype(np.int32)),
+                           "out_d": flat(u["d"].astype(np.int32)), "mask": flat(u["inlier"].copy()),
+                           "R": torch.from_numpy(u["R"].copy()), "t": torch.from_numpy(u["t"].copy())})
+
+    def __missing__(self, key):
+        self._fill()
+        return dict.__getitem__(self, key)
+
+
 class SequenceTracker:
-    """End-to-end tracking of a frame sequence from HOST buffers (the e2e number of bench.py).
-
-    Frames (descriptors uint8 [F, N, 32], keypoints float32 [F, N, 2], pinned) are uploaded
-    once each; the F-1 consecutive pairs are processed in `chunks` pieces so the upload of
+    """End-to-end tracking of ONE frame sequence from HOST buffers, in `chunks` pieces so that the upload of
     chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c (three streams).
-    Results land in pinned host buffers: per pair the match count, winning hypothesis and
-    inlier count, and per match (compact stride max_matches) queryIdx/trainIdx/distance/inlier.
 
-    use_graph: the whole step (uploads, ~10 launches per chunk, downloads, on three streams) is
-    captured into ONE CUDA graph on its second call with the same host buffers and replayed
-    afterwards — the eager step is bound by host launch overhead (~60 stream operations), not by
-    the device.  The caller keeps writing new frames into the same pinned staging buffers.
+    Frames (descriptors uint8 [F, N, 32], keypoints float32 [F, N, 2], pinned) are uploaded once each; every
+    chunk ends with the record kernel and ONE device->host copy of its records (it was seven copies per chunk).
+    ``run`` returns a RecordView over the pinned record buffer.  For several steps in flight use SequencePipeline.
     """
 
     def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
@@ -641,19 +734,19 @@ class SequenceTracker:
         chunks = max(1, min(chunks, self.n_pairs))
         self.bounds = [(self.n_pairs * c // chunks, self.n_pairs * (c + 1) // chunks) for c in range(chunks)]
         self.s_up, self.s_down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        P, S = self.n_pairs, cfg.max_matches
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-        self.out = {"count": pin(P, torch.int32), "best_h": pin(P, torch.int32), "best_count": pin(P, torch.int32),
-                    "out_q": pin(P * S, torch.int32), "out_t": pin(P * S, torch.int32),
-                    "out_d": pin(P * S, torch.int32), "mask": pin(P * S, torch.uint8)}
+        self.rec_bytes = record_bytes(cfg.max_matches)
+        self.rec_dev = torch.empty((self.n_pairs, self.rec_bytes), dtype=torch.uint8, device=self.dev)
+        self.rec_host = torch.empty((self.n_pairs, self.rec_bytes), dtype=torch.uint8).pin_memory()
+        self.out = RecordView(self.rec_host, cfg.max_matches)
         self._batches = None
         self.h2d_bytes = int(self.F * frame_rows * (DESC_BYTES + 8))
-        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.out.values()))
+        self.d2h_bytes = int(self.rec_host.numel())
         self.use_graph = use_graph
         self._graph, self._graph_key, self._eager_key = None, None, None
 
     def run(self, desc_host, kp_host, counts: np.ndarray):
         """desc_host: pinned uint8 [F*N, 32]; kp_host: pinned float32 [F*N, 2]; counts: rows used per frame."""
+        self.out = RecordView(self.rec_host, self.cfg.max_matches)
         if not self.use_graph:
             return self._run_eager(desc_host, kp_host, counts)
         key = (desc_host.data_ptr(), kp_host.data_ptr(), np.asarray(counts).tobytes())
@@ -689,97 +782,138 @@ class SequenceTracker:
                 ev = torch.cuda.Event()
                 ev.record(self.s_up)
                 ups.append(ev)
-        self.h2d_bytes = int(self.F * N * (DESC_BYTES + 8))
-        S = self.cfg.max_matches
         for c, (lo, hi) in enumerate(self.bounds):
             main.wait_event(ups[c])
-            res = self.fe.run(self._batches[c])
+            res = self.fe.run(self._batches[c], records=self.rec_dev[lo:hi], pair_id0=lo)
             done = torch.cuda.Event()
             done.record(main)
             keep.append(res)
             with torch.cuda.stream(self.s_down):
                 self.s_down.wait_event(done)
-                o = self.out
-                o["count"][lo:hi].copy_(res.sel.count, non_blocking=True)
-                o["best_h"][lo:hi].copy_(res.best_h, non_blocking=True)
-                o["best_count"][lo:hi].copy_(res.best_count, non_blocking=True)
-                o["out_q"][lo * S:hi * S].copy_(res.sel.out_q, non_blocking=True)
-                o["out_t"][lo * S:hi * S].copy_(res.sel.out_t, non_blocking=True)
-                o["out_d"][lo * S:hi * S].copy_(res.sel.out_d, non_blocking=True)
-                o["mask"][lo * S:hi * S].copy_(res.inlier_mask, non_blocking=True)
+                self.rec_host[lo:hi].copy_(self.rec_dev[lo:hi], non_blocking=True)      # the chunk's ONE download
         main.wait_stream(self.s_down)
         self._keep = keep                                          # device tensors stay alive until the next run
         return self.out
 
 
 class SequencePipeline:
-    """End-to-end consecutive-frame tracking from pinned host buffers with `depth` steps in flight.
+    """End-to-end consecutive-frame tracking from pinned host buffers with `depth` steps in flight — the
+    library's throughput front door (bench.py's ``e2e`` is ``submit`` x K + ``result``).
 
-    Three streams: uploads, kernels, downloads.  The upload of step s+1 and the download of step s-1
-    overlap the kernels of step s, but the kernels of different steps never interleave: they all run on
-    ONE stream (a step's library calls are captured once per slot in a CUDA graph and replayed).  With
-    two whole-step graphs on two streams (SequenceTracker x 2) the kernels of neighbouring steps did
-    overlap, and how they happened to interleave moved the end-to-end rate between 403k and 439k
-    pairs/s; a persistent one-CTA-per-SM kernel such as K2s wants the machine to itself.
+    A step = upload of the F frames (descriptors + keypoints), the hot-path kernels on the F-1 consecutive
+    pairs, the record kernel, and ONE device->host copy of the records (``record_bytes(max_matches)`` per pair).
 
-    submit() is asynchronous and returns the slot; result(slot) waits for that slot's download and
-    returns its pinned output dict (valid until the slot is submitted again)."""
+    schedule = "interleaved" (default): every slot has its own stream, device / pinned buffers and Frontend
+      (workspace); a step is four operations on that stream — two uploads, ONE CUDA graph with every kernel of
+      the step, one download.  Steps of different slots overlap freely: the upload of step s+1 and the download of
+      step s-1 run under the kernels of step s, and so may the first / last kernels of neighbouring steps, which
+      hides the gaps between back-to-back graph launches (measured: 437k against 427k pairs/s).
+    schedule = "serial": three streams (uploads, kernels, downloads); copies overlap, but the kernels of all steps
+      run on ONE stream and never interleave; accepts different host buffers on every call without re-capture.
+
+    submit() is asynchronous and returns the slot; result(slot) waits for that slot's download and returns a
+    RecordView over its pinned record buffer (valid until the slot is submitted again)."""
 
     def __init__(self, n_frames: int, frame_rows: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
-                 depth: int = 2, device=None, use_graph: bool = True):
+                 depth: int = 3, device=None, use_graph: bool = True, schedule: str = "interleaved", after_compute=None):
         torch = _capi.require_cuda()
         if not cfg.max_matches:
             raise ValueError("SequencePipeline needs max_matches (compact output stride)")
-        self.torch, self.cfg = torch, cfg
+        if schedule not in ("interleaved", "serial"):
+            raise ValueError("schedule must be 'interleaved' or 'serial'")
+        self.torch, self.cfg, self.schedule = torch, cfg, schedule
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.F, self.N, self.n_pairs = n_frames, frame_rows, n_frames - 1
         self.depth = max(1, depth)
-        self.fe = Frontend(cfg, variant=variant)        # kernels are serialised on one stream: one workspace serves every slot
+        self.after_compute = after_compute       # optional callable(slot dict) enqueued after the kernels (e.g. a collective)
+        shared_fe = Frontend(cfg, variant=variant) if schedule == "serial" else None   # one stream: one workspace serves every slot
         self.s_up, self.s_compute, self.s_down = (torch.cuda.Stream(self.dev) for _ in range(3))
-        P, S = self.n_pairs, cfg.max_matches
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        P = self.n_pairs
+        self.rec_bytes = record_bytes(cfg.max_matches)
         self.slots = []
         for _ in range(self.depth):
             self.slots.append({
                 "desc": torch.empty((n_frames * frame_rows, DESC_BYTES), dtype=torch.uint8, device=self.dev),
                 "kp": torch.empty((n_frames * frame_rows, 2), dtype=torch.float32, device=self.dev),
-                "out": {"count": pin(P, torch.int32), "best_h": pin(P, torch.int32), "best_count": pin(P, torch.int32),
-                        "out_q": pin(P * S, torch.int32), "out_t": pin(P * S, torch.int32),
-                        "out_d": pin(P * S, torch.int32), "mask": pin(P * S, torch.uint8)},
+                "rec_dev": torch.empty((P, self.rec_bytes), dtype=torch.uint8, device=self.dev),
+                "rec_host": torch.empty((P, self.rec_bytes), dtype=torch.uint8).pin_memory(),
+                "fe": shared_fe or Frontend(cfg, variant=variant),
+                "stream": torch.cuda.Stream(self.dev) if schedule == "interleaved" else None,
                 "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event(),
                 "used": False, "batch": None, "graph": None, "res": None})
+        self.fe = self.slots[0]["fe"]
         self.h2d_bytes = int(self.F * frame_rows * (DESC_BYTES + 8))
-        self.d2h_bytes = int(sum(v.numel() * v.element_size() for v in self.slots[0]["out"].values()))
+        self.d2h_bytes = int(P * self.rec_bytes)
         self.use_graph = use_graph
         self._counts = None
         self._next = 0
 
+    # ---- shared -----------------------------------------------------------------------------------------
+    def _run_kernels(self, sl):
+        sl["res"] = sl["fe"].run(sl["batch"], records=sl["rec_dev"], pair_id0=0)
+        if self.after_compute is not None:
+            self.after_compute(sl)
+
     def _prepare(self, counts: np.ndarray):
-        """(Re)build the per-slot batches and graphs for this frame-size vector."""
+        """(Re)build the per-slot batches (and, for the serial schedule, the kernel graphs) for this frame-size vector."""
         torch = self.torch
         self._counts = np.array(counts, copy=True)
         torch.cuda.synchronize()
         for sl in self.slots:
             sl["batch"] = sequence_batch(sl["desc"], sl["kp"], self._counts, 0, self.n_pairs, self.N)
             sl["graph"], sl["used"] = None, False
-            with torch.cuda.stream(self.s_compute):
-                sl["res"] = self.fe.run(sl["batch"])                      # eager once: lazy init, workspace
-            self.s_compute.synchronize()
-            if self.use_graph:
+            st = sl["stream"] or self.s_compute
+            with torch.cuda.stream(st):
+                self._run_kernels(sl)                                     # eager once: lazy init, workspace
+            st.synchronize()
+            if self.use_graph and self.schedule == "serial":
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.s_compute):
-                    sl["res"] = self.fe.run(sl["batch"])
+                    self._run_kernels(sl)
                 sl["graph"] = g
         torch.cuda.synchronize()
 
-    def submit(self, desc_host, kp_host, counts: np.ndarray, after_compute=None) -> int:
+    def submit(self, desc_host, kp_host, counts: np.ndarray) -> int:
         """desc_host: pinned uint8 [F*N, 32]; kp_host: pinned float32 [F*N, 2]; counts: rows used per frame."""
-        torch = self.torch
         if self._counts is None or not np.array_equal(self._counts, counts):
             self._prepare(counts)
         i = self._next % self.depth
         self._next += 1
         sl = self.slots[i]
+        if self.schedule == "serial":
+            self._submit_serial(sl, desc_host, kp_host)
+        else:
+            self._submit_interleaved(sl, desc_host, kp_host)
+        sl["used"] = True
+        return i
+
+    # ---- interleaved: the slot's stream carries upload -> kernel graph -> download ------------------------
+    def _submit_interleaved(self, sl, desc_host, kp_host):
+        torch = self.torch
+        st = sl["stream"]
+        if self.use_graph and sl["graph"] is None:
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, stream=st):
+                    self._run_kernels(sl)
+                sl["graph"] = g
+            except Exception:                                  # e.g. a collective hook the NCCL build cannot capture
+                torch.cuda.synchronize()
+                self.use_graph = False
+        with torch.cuda.stream(st):
+            sl["desc"].copy_(desc_host, non_blocking=True)     # any pinned host buffers: the copies are not part of the graph
+            sl["kp"].copy_(kp_host, non_blocking=True)
+            if sl["graph"] is not None:
+                sl["graph"].replay()
+            else:
+                self._run_kernels(sl)
+            sl["rec_host"].copy_(sl["rec_dev"], non_blocking=True)      # the step's ONE download
+            sl["downloaded"].record(st)
+
+    # ---- serial: copies overlap, kernels on one stream ---------------------------------------------------
+    def _submit_serial(self, sl, desc_host, kp_host):
+        torch = self.torch
         if sl["used"]:
             self.s_up.wait_event(sl["computed"])            # the slot's device inputs are free again
         with torch.cuda.stream(self.s_up):
@@ -793,30 +927,111 @@ class SequencePipeline:
             if sl["graph"] is not None:
                 sl["graph"].replay()
             else:
-                sl["res"] = self.fe.run(sl["batch"])
-            if after_compute is not None:
-                after_compute(sl["res"])
+                self._run_kernels(sl)
             sl["computed"].record(self.s_compute)
         self.s_down.wait_event(sl["computed"])
         with torch.cuda.stream(self.s_down):
-            res, o = sl["res"], sl["out"]
-            o["count"].copy_(res.sel.count, non_blocking=True)
-            o["best_h"].copy_(res.best_h, non_blocking=True)
-            o["best_count"].copy_(res.best_count, non_blocking=True)
-            o["out_q"].copy_(res.sel.out_q, non_blocking=True)
-            o["out_t"].copy_(res.sel.out_t, non_blocking=True)
-            o["out_d"].copy_(res.sel.out_d, non_blocking=True)
-            o["mask"].copy_(res.inlier_mask, non_blocking=True)
+            sl["rec_host"].copy_(sl["rec_dev"], non_blocking=True)      # the step's ONE download
             sl["downloaded"].record(self.s_down)
-        sl["used"] = True
-        return i
 
     def result(self, slot: int):
-        self.slots[slot]["downloaded"].synchronize()
-        return self.slots[slot]["out"]
+        sl = self.slots[slot]
+        sl["downloaded"].synchronize()
+        return RecordView(sl["rec_host"], self.cfg.max_matches)
 
     def streams(self):
+        if self.schedule == "interleaved":
+            return tuple(sl["stream"] for sl in self.slots)
         return (self.s_up, self.s_compute, self.s_down)
+
+
+class MapSweep:
+    """BASELINE config #5 on one GPU: one query frame against EVERY keyframe of a persistent map (the loop of
+    MapRelocalizer.relocalize, persistent_map.py:244-309, without the BoW cut to max_candidates), the map's
+    descriptors and keypoints resident on the device.  Per query: ONE Hamming launch over all keyframes (pair p =
+    keyframe p as the query side, the current frame as the train side, like the reference's
+    ``matcher.match(kf.descriptors, descriptors)``, :266; every block expanded once), the cross-check selection
+    sorted by distance with the top `max_matches` kept (:270) and the untruncated match count, the ranking of the
+    keyframes by that count on the device, geometric verification (RANSAC E + refit + decomposition) of the best
+    `top` only (mirrors max_candidates, :242), and `top` candidate records."""
+
+    def __init__(self, kf_desc, kf_kp, frame_ids, cfg: FrontendConfig, *, top: int = 5, max_query_rows: int = 2048,
+                 device=None, variant: int = _capi.VARIANT_I8MMA1):
+        torch = _capi.require_cuda()
+        if not cfg.max_matches:
+            raise ValueError("MapSweep needs max_matches (compact output stride)")
+        self.cfg, self.top = cfg, int(top)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_kf = len(kf_desc)
+        sizes = np.array([len(d) for d in kf_desc], np.int64)
+        self.off = np.zeros(self.n_kf + 1, np.int32)
+        np.cumsum(sizes, out=self.off[1:])
+        self.q_row0, self.max_query_rows = int(self.off[-1]), int(max_query_rows)
+        rows = self.q_row0 + self.max_query_rows
+        self.desc = torch.zeros((rows, DESC_BYTES), dtype=torch.uint8, device=self.dev)
+        self.kp = torch.zeros((rows, 2), dtype=torch.float32, device=self.dev)
+        if self.n_kf:
+            self.desc[: self.q_row0].copy_(torch.from_numpy(np.concatenate([_prep_desc(d) for d in kf_desc], axis=0)))
+            self.kp[: self.q_row0].copy_(torch.from_numpy(np.concatenate([np.asarray(k, np.float32).reshape(-1, 2) for k in kf_kp], axis=0)))
+        self.frame_ids = torch.from_numpy(np.asarray(frame_ids, np.int32).copy()).to(self.dev)
+        self.max_kf_rows = int(sizes.max()) if self.n_kf else 0
+        self.matcher, self.ransac, self.pose = HammingMatcher(variant=variant), EssentialRansac(), PoseRecovery()
+        self._batches = {}
+        self.nq = 0
+        self.last = None
+
+    def query_desc_slot(self):
+        return self.desc[self.q_row0:]
+
+    def query_kp_slot(self):
+        return self.kp[self.q_row0:]
+
+    def set_query_rows(self, n: int):
+        if not 0 < n <= self.max_query_rows:
+            raise ValueError("query frame does not fit the slot")
+        self.nq = int(n)
+
+    def set_query(self, desc_dev, kp_dev):
+        n = int(desc_dev.shape[0])
+        self.set_query_rows(n)
+        self.desc[self.q_row0:self.q_row0 + n].copy_(desc_dev, non_blocking=True)
+        self.kp[self.q_row0:self.q_row0 + n].copy_(kp_dev.reshape(-1, 2), non_blocking=True)
+
+    def _batch(self, n: int) -> PairBatch:
+        if n not in self._batches:
+            torch, K = _capi.require_cuda(), self.n_kf
+            t_off = (np.arange(K + 1, dtype=np.int64) * n).astype(np.int32)
+            shared = SharedBlocks.build(np.concatenate([self.off[:-1], [self.q_row0]]), np.concatenate([np.diff(self.off), [n]]),
+                                        np.arange(K), np.full(K, K), self.dev)
+            pack = torch.from_numpy(np.concatenate([self.off, t_off, self.off[:-1], np.full(K, self.q_row0, np.int32)]).astype(np.int32)).to(self.dev)
+            self._batches[n] = PairBatch(q_desc=self.desc, t_desc=self.desc, q_off=pack[:K + 1], t_off=pack[K + 1:2 * K + 2],
+                                         q_off_host=self.off, t_off_host=t_off, kp_q=self.kp, kp_t=self.kp,
+                                         q_src=pack[2 * K + 2:3 * K + 2], t_src=pack[3 * K + 2:], shared=shared)
+        return self._batches[n]
+
+    def run(self, records=None, counts_out=None):
+        """All launches on the current stream, nothing touches the host.  records: device uint8 [top, record_bytes];
+        counts_out: device int32 [n_kf] (per-keyframe cross-check match counts).  -> dict of device tensors."""
+        torch = _capi.require_cuda()
+        c, S, k = self.cfg, self.cfg.max_matches, min(self.top, max(self.n_kf, 1))
+        b = self._batch(self.nq)
+        keys = self.matcher.knn2(b)
+        sel = self.matcher.select(b, keys, use_ratio=False, use_cross=True, sort_by_distance=True, max_matches=S,
+                                  with_corr=True, compact=True, with_total=True)
+        top_idx, c_off, c_cnt, top_id = rank_pairs(sel.total, k, ids=self.frame_ids, sel_count=sel.count, stride=S, with_ids=True)
+        E = self.ransac.hypotheses(sel.corr, c_off, c_cnt, k, c.hypotheses, seed=c.seed, pair_ids=top_id)   # keyed by frame id: sharding-independent
+        th2 = c.threshold ** 2
+        counts = self.ransac.score(sel.corr, c_off, c_cnt, k, E, th2, precision=c.precision, max_m=S)
+        best_h, best_c, mask = self.ransac.select(counts, sel.corr, c_off, c_cnt, k, E, th2)
+        E_refit, R, t, votes = self.pose.recover(sel.corr, c_off, c_cnt, k, S, mask=mask)
+        if records is not None:
+            pack_records(records, sel, best_h, best_c, mask, R, t, n_records=k, pair_ids=self.frame_ids, src_pair=top_idx,
+                         count_total=sel.total)
+        if counts_out is not None:
+            counts_out.copy_(sel.total, non_blocking=True)
+        self.last = {"keys": keys, "sel": sel, "top_idx": top_idx, "c_off": c_off, "c_count": c_cnt, "best_h": best_h,
+                     "best_count": best_c, "mask": mask, "R": R, "t": t, "E": E, "counts": counts}
+        return self.last
 
 
 def pipe_microbench(which: str, iters: int = 2000, ctas_per_sm: int = 8, repeats: int = 5):

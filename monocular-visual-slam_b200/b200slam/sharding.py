@@ -1,12 +1,21 @@
-"""Multi-GPU plumbing: frame pairs are independent, so ranks take contiguous blocks of
-the pair batch and the only collective is one all-gather of fixed-size result records
-(SURVEY.md §8e).  Works with NCCL (one process per B200) and with gloo on CPU (tests).
+"""Multi-GPU path: frame pairs are independent, so ranks take contiguous blocks of the pair batch (or of the
+map's keyframes) and the only collective is ONE all-gather of fixed-size result records.
+One process per B200 (torchrun), NCCL over NVLink; the same classes run over gloo on CPU tensors (tests).
+
+* ``shard_bounds``        who owns what.
+* ``RecordGather``        the persistent all-gather buffer: every rank's last kernel writes its records straight
+                          into its own slice (``local``), ``all_gather()`` is the in-place collective.
+* ``ShardedFrontend``     match -> select -> RANSAC -> pose -> records on this rank's pairs + the gather, captured
+                          as ONE CUDA graph (the NCCL all-gather is a node of it): BASELINE configs #2 / #3.
+* ``ShardedSweep``        relocalization sweep (config #5): the map's keyframes sharded by id and resident on each
+                          GPU, the query broadcast once, every rank verifies its local top-k, the gathered
+                          candidates hold the global top-k.
 """
 from __future__ import annotations
 
 import numpy as np
 
-RECORD_WIDTH = 4  # per pair: (n_matches, best_h, inlier_count, pair_id)
+RECORD_WIDTH = 4  # legacy int32 record: (n_matches, best_h, inlier_count, pair_id)
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
@@ -18,30 +27,226 @@ def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_capacity(n_items: int, world: int) -> int:
+    return -(-n_items // world) if world > 0 else n_items
+
+
 def pack_records(pair_ids, n_matches, best_h, inlier_count):
-    """-> (n_local, RECORD_WIDTH) int32 array."""
+    """-> (n_local, RECORD_WIDTH) int32 array (the small legacy record; the full record is csrc/records.cu)."""
     return np.stack([np.asarray(n_matches, np.int32), np.asarray(best_h, np.int32),
                      np.asarray(inlier_count, np.int32), np.asarray(pair_ids, np.int32)], axis=1)
 
 
 def gather_records(local, n_items: int, group=None):
-    """All-gather per-pair result records (torch tensor, (n_local, W) int32, on the
-    backend's device) from every rank; returns the (n_items, W) tensor ordered by pair id.
-    Blocks are padded to the largest shard so a single fixed-size collective suffices."""
-    import torch
+    """All-gather per-pair result records (torch tensor, (n_local, W), on the backend's device) from every rank;
+    returns the (n_items, W) tensor ordered by pair id.  One fixed-size collective (shards padded to the largest)."""
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
-    world = dist.get_world_size(group)
-    cap = max(shard_bounds(n_items, r, world)[1] - shard_bounds(n_items, r, world)[0] for r in range(world))
-    width = local.shape[1]
-    send = torch.full((cap, width), -1, dtype=local.dtype, device=local.device)
-    send[: local.shape[0]] = local
-    recv = torch.empty((world * cap, width), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    parts = []
-    for r in range(world):
-        lo, hi = shard_bounds(n_items, r, world)
-        parts.append(recv[r * cap: r * cap + (hi - lo)])
-    return torch.cat(parts, dim=0)
+    g = RecordGather(n_items, int(local.shape[1]), dtype=local.dtype, device=local.device, group=group, pad_value=-1)
+    g.local[: local.shape[0]] = local
+    g.all_gather()
+    return g.ordered()
+
+
+class RecordGather:
+    """Persistent gather buffer [world, cap, width]: ``local`` (this rank's [cap, width] slice) is where the last
+    kernel of a step writes; ``all_gather()`` completes the other slices in place (NCCL recognises
+    sendbuff == recvbuff + rank * count and moves nothing locally).  ``ordered()`` drops the padding."""
+
+    def __init__(self, n_items: int, width: int, *, dtype=None, device=None, group=None, pad_value=0):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.dist_on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.dist_on else 1
+        self.rank = dist.get_rank(group) if self.dist_on else 0
+        self.n_items, self.width = int(n_items), int(width)
+        self.cap = shard_capacity(self.n_items, self.world)
+        self.lo, self.hi = shard_bounds(self.n_items, self.rank, self.world)
+        self.buf = torch.full((self.world, self.cap, self.width), pad_value, dtype=dtype or torch.uint8, device=device)
+        self.local = self.buf[self.rank]
+
+    @property
+    def n_local(self) -> int:
+        return self.hi - self.lo
+
+    def all_gather(self):
+        """Enqueue the collective on the current stream (capturable into a CUDA graph with NCCL)."""
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(self.buf.view(-1), self.local.reshape(-1), group=self.group)
+        return self.buf
+
+    def ordered(self):
+        """[n_items, width] in pair order (a copy; padding rows of short shards dropped)."""
+        import torch
+
+        if self.cap * self.world == self.n_items:
+            return self.buf.reshape(self.n_items, self.width)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.n_items, r, self.world)
+            parts.append(self.buf[r, : hi - lo])
+        return torch.cat(parts, dim=0)
+
+
+class ShardedFrontend:
+    """The hot path on this rank's block of a global pair batch + the gather of every rank's result records.
+
+    ``n_pairs_global`` pairs are split with ``shard_bounds``; the caller builds the PairBatch of ITS pairs
+    (``self.lo .. self.hi``).  ``step(batch)`` runs match -> select -> hypotheses -> score -> winner -> refit ->
+    decomposition, the record kernel writes into this rank's slice of the gather buffer, and the all-gather
+    follows on the same stream.  ``capture(batch)`` records exactly that — collective included — into one CUDA
+    graph (``replay()``); if the NCCL build cannot be captured the kernels are replayed and the collective is
+    issued eagerly behind them (``gather_in_graph`` says which).  After a step every rank holds every pair's
+    record (``records()`` -> device uint8 [n_pairs_global, record_bytes])."""
+
+    def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None):
+        import dataclasses
+
+        from . import _capi
+        from .frontend import Frontend, record_bytes
+
+        torch = _capi.require_cuda()
+        if not cfg.max_matches:
+            raise ValueError("ShardedFrontend needs max_matches (record stride)")
+        self.cfg = dataclasses.replace(cfg, with_pose=True)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.fe = Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant)
+        self.rec_bytes = record_bytes(cfg.max_matches)
+        self.gather = RecordGather(n_pairs_global, self.rec_bytes, dtype=torch.uint8, device=self.dev, group=group)
+        self.gather.buf.view(torch.int32).reshape(self.gather.world, self.gather.cap, -1)[:, :, 3] = -1   # padding slots: pair id -1
+        self.lo, self.hi, self.world, self.rank = self.gather.lo, self.gather.hi, self.gather.world, self.gather.rank
+        self._graph, self._batch, self.res = None, None, None
+        self.gather_in_graph = False
+
+    def step(self, batch, K=None):
+        if batch.n_pairs != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} owns pairs [{self.lo}, {self.hi}) but the batch has {batch.n_pairs}")
+        self.res = self.fe.run(batch, K=K, records=self.gather.local[: batch.n_pairs], pair_id0=self.lo)
+        self.gather.all_gather()
+        return self.res
+
+    def capture(self, batch, K=None, collective_in_graph: bool = True):
+        """One eager step (lazy init, workspaces, NCCL warm-up), then the capture."""
+        import torch
+
+        self.step(batch, K)
+        torch.cuda.synchronize()
+        self._batch, self._K = batch, K
+        g = torch.cuda.CUDAGraph()
+        self.gather_in_graph = False
+        if collective_in_graph and self.world > 1:
+            try:
+                with torch.cuda.graph(g):
+                    self.step(batch, K)
+                self.gather_in_graph = True
+            except Exception:                      # NCCL / torch build that cannot capture the collective
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+        if not self.gather_in_graph:
+            with torch.cuda.graph(g):
+                self.res = self.fe.run(batch, K=K, records=self.gather.local[: batch.n_pairs], pair_id0=self.lo)
+        self._graph = g
+        torch.cuda.synchronize()
+        return self.gather_in_graph
+
+    def replay(self):
+        self._graph.replay()
+        if not self.gather_in_graph:
+            self.gather.all_gather()
+        return self.res
+
+    def records(self):
+        return self.gather.ordered()
+
+
+class ShardedSweep:
+    """BASELINE config #5 on N GPUs: keyframes sharded by id (contiguous blocks), each shard resident on its GPU
+    (``MapSweep``), the query frame broadcast from rank 0, every rank cross-check-matches the query against
+    ITS keyframes, verifies its local top-k geometrically and contributes k candidate records + its per-keyframe
+    match counts to ONE all-gather.  The global top-k by match count is among the world x k gathered candidates."""
+
+    def __init__(self, kf_desc, kf_kp, frame_ids, cfg, *, top: int = 5, max_query_rows: int = 2048, group=None, device=None,
+                 n_keyframes_global: int | None = None):
+        """kf_desc / kf_kp / frame_ids: THIS rank's keyframes (lists of (n_i, 32) uint8 / (n_i, 2) float32, ids)."""
+        from . import _capi
+        from .frontend import MapSweep, record_bytes
+
+        torch = _capi.require_cuda()
+        import torch.distributed as dist
+
+        self.group = group
+        self.dist_on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.dist_on else 1
+        self.rank = dist.get_rank(group) if self.dist_on else 0
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.sweep = MapSweep(kf_desc, kf_kp, frame_ids, cfg, top=top, max_query_rows=max_query_rows, device=self.dev)
+        self.top, self.stride = top, cfg.max_matches
+        self.n_global = n_keyframes_global if n_keyframes_global is not None else len(kf_desc) * self.world
+        self.cap = shard_capacity(self.n_global, self.world)
+        rb = record_bytes(cfg.max_matches)
+        self.slot_bytes = top * rb + ((4 * self.cap + 63) // 64) * 64          # k candidate records | per-keyframe counts
+        self.gather = RecordGather(self.world, self.slot_bytes, dtype=torch.uint8, device=self.dev, group=group)
+        slot = self.gather.local[0]
+        self.cand = slot[: top * rb].view(top, rb)
+        self.counts = slot[top * rb: top * rb + 4 * self.cap].view(torch.int32)
+        self.counts.fill_(-1)
+        self._graph = None
+
+    def query(self, q_desc_dev=None, q_kp_dev=None, n_rows: int | None = None):
+        """Rank 0 passes the query frame (device uint8 [n, 32], float32 [n, 2]); the others pass None."""
+        import torch
+        import torch.distributed as dist
+
+        sw = self.sweep
+        if self.rank == 0 and q_desc_dev is not None:
+            sw.set_query(q_desc_dev, q_kp_dev)
+        if self.world > 1:                          # the 64 KB + 16 KB query, once
+            dist.broadcast(sw.query_desc_slot(), src=0, group=self.group)
+            dist.broadcast(sw.query_kp_slot(), src=0, group=self.group)
+        sw.run(records=self.cand, counts_out=self.counts[: sw.n_kf])
+        self.gather.all_gather()
+        return self.gather.buf
+
+    def capture(self):
+        import torch
+
+        self.query()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self.query()
+            self._graph = g
+        except Exception:
+            torch.cuda.synchronize()
+            self._graph = None
+        return self._graph is not None
+
+    def replay(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self.query()
+
+    def result_host(self):
+        """-> (per-keyframe match counts in global keyframe order, the global top-k candidates as a dict of arrays
+        sorted by (-count, frame id))."""
+        from .frontend import unpack_records
+
+        buf = self.gather.buf.cpu().numpy().reshape(self.world, self.slot_bytes)
+        rb = (self.slot_bytes - ((4 * self.cap + 63) // 64) * 64) // self.top
+        counts, cands = [], []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.n_global, r, self.world)
+            counts.append(buf[r, self.top * rb: self.top * rb + 4 * self.cap].copy().view(np.int32)[: hi - lo])
+            cands.append(buf[r, : self.top * rb].reshape(self.top, rb))
+        rec = unpack_records(np.concatenate(cands, axis=0), self.stride)
+        ok = np.flatnonzero(rec["pair_id"] >= 0)
+        order = ok[np.lexsort((rec["pair_id"][ok], -rec["n_matches"][ok]))][: self.top]
+        return np.concatenate(counts), {k: v[order] for k, v in rec.items()}

@@ -40,19 +40,20 @@ int hamming_popc_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off
                         int max_nq, int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best,
                         int t_split, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt);
+size_t hamming_i8_workspace_bytes(int n_pairs, int total_nq, int max_nq, int max_nt, int t_split);
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
-                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
-                      size_t workspace_bytes, int single, cudaStream_t st);
+                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, int t_split,
+                      void* workspace, size_t workspace_bytes, int single, cudaStream_t st);
 
-size_t hamming_i8_shared_workspace_bytes(int total_tiles);
+size_t hamming_i8_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split);
 int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
                              const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                              const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                              int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                             uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
-                             cudaStream_t st);
+                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st);
+void hamming_i8_last_plan(int* subs, int* t_split, int* grid);
 
 void hamming_i8_set_debug(unsigned long long* dev_buf, int mode);
 int hamming_i8_timing(int enable, float* last_ms);
@@ -168,21 +169,25 @@ int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const
   }
   if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1) {
     return hamming_i8_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt, max_nq,
-                             max_nt, fwd_best, fwd_second, bwd_best, workspace, workspace_bytes,
+                             max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
                              variant == B2S_VARIANT_I8MMA1, st);
   }
   set_error("Hamming variant %d is not built into this library", variant);
   return B2S_ERR_UNSUPPORTED;
 }
 
-size_t b2s_hamming_shared_workspace_bytes(int total_tiles) { return b2s::hamming_i8_shared_workspace_bytes(total_tiles); }
+size_t b2s_hamming_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
+  return b2s::hamming_i8_shared_workspace_bytes(total_tiles, n_pairs, total_nq, max_nq, max_nt, t_split);
+}
+
+void b2s_hamming_last_plan(int* subs, int* t_split, int* grid) { b2s::hamming_i8_last_plan(subs, t_split, grid); }
 
 int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
                             const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                             const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                             int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                            uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(n_pairs >= 0 && n_blocks >= 0 && total_tiles >= 0 && total_nq >= 0 && total_nt >= 0 && max_nq >= 0 &&
                   max_nt >= 0 && max_block_rows >= 0, "negative size");
@@ -195,12 +200,13 @@ int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const 
   B2S_REQUIRE(((uintptr_t)desc & 15u) == 0, "descriptor buffer must be 16-byte aligned");
   return hamming_i8_shared_launch(desc, blk_row0, blk_rows, blk_tile0, n_blocks, total_tiles, max_block_rows, q_xtile,
                                   t_xtile, q_off, t_off, n_pairs, total_nq, total_nt, max_nq, max_nt, fwd_best,
-                                  fwd_second, bwd_best, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                                  fwd_second, bwd_best, t_split, workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
   if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1)
-    return b2s::hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
+    return b2s::hamming_i8_workspace_bytes(n_pairs, total_nq, max_nq, max_nt, variant == B2S_VARIANT_I8MMA1 ? t_split : 1);
   return b2s_hamming_workspace_bytes(total_nq, t_split);
 }
 

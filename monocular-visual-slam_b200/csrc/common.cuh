@@ -32,6 +32,16 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+// true exactly once per (flag array, current device): function attributes such as the dynamic shared-memory
+// opt-in are per device, and one process may drive several GPUs (HammingMatcher(device=...)).  A race between
+// host threads only repeats an idempotent call.
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
 void note_launch(int n = 1);  // counts kernels launched by this library (b2s_launch_count)
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;

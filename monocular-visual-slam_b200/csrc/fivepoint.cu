@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kFpThreads) five_point_kernel(const float4* __
   const int pair = blockIdx.y;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   double* eo = E_out + ((size_t)pair * S + s) * (kFpMaxSol * 9);
   int idx[5];
@@ -358,11 +358,9 @@ int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (n_pairs == 0 || S == 0) return B2S_OK;
   const size_t smem = (size_t)10 * 20 * kFpThreads * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (first_use_on_device(attr_set))
     B2S_CUDA(cudaFuncSetAttribute(five_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   dim3 grid((S + kFpThreads - 1) / kFpThreads, n_pairs);
   five_point_kernel<<<grid, kFpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(corr), c_off, c_count, S, samples_in, seed, samples_out, E_out, n_sol);

@@ -273,6 +273,11 @@ struct I8Params {
   unsigned long long* dbg;  // optional per-CTA stall counters (b2s_hamming_i8_debug), else nullptr
   int mode;                 // diagnostics only: bit 0 = epilogue does no work, bit 1 = ring is loaded once,
                             // (single-product kernel) bit 2 = no column butterfly, bit 3 = no row top-2
+  // single-product kernel only: t_split > 1 cuts every (pair, query block) into t_split work items along the
+  // train axis; item `part` writes its rows' top-2 to partial[part * total_nq + row] and a merge kernel folds them
+  int t_split;
+  int total_nq;
+  uint2* __restrict__ partial;
 };
 // dbg layout per CTA (8 x u64): [0] MMA thread total, [1] MMA wait tempty, [2] MMA wait full/qfull,
 // [3] producer wait empty, [4] epilogue warp 2 total, [5] epilogue wait tfull, [6] tile pairs, [7] -
@@ -650,43 +655,58 @@ __device__ __forceinline__ void colmin_warp(uint32_t (&y)[64], int lane) {
   y[1] -= cfix + 0x00020002u;                                            // columns 4L+2 | 4L+3
 }
 
-template <int EPI, bool DBG>
+// SUBS = query sub-tiles (128 rows each) that stay in shared memory per work item: 2 (4-stage train ring) or
+// 4 (2-stage ring: a train tile then feeds FOUR tile pairs, ~3400 clk, which still covers the L2 latency of the
+// next one).  With 4 the L2 -> SM operand traffic per tile pair drops from 17 + 2.25 KB to 8.5 + 2.25 KB and
+// epilogue set e simply owns sub-tile e (TMEM stage e), so nothing is merged at the end of an item.
+template <int SUBS> struct I8sCfg {
+  static constexpr int kStages = SUBS == 4 ? 2 : 4;
+  static constexpr size_t kSmem = (size_t)SUBS * kI8sQTileBytes + (size_t)kStages * kI8TileBytes + kI8ChunkBytes +
+                                  8 * (kI8sGo + 12) + 16 + (SUBS == 2 ? 4 * kI8Tile * sizeof(uint2) : 0) +
+                                  16 * 32 * sizeof(uint4);
+};
+
+template <int EPI, bool DBG, int SUBS>
 __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
+  static_assert(SUBS == 2 || (SUBS == 4 && EPI == 1), "4 sub-tiles per item: 16x256b epilogue only");
+  constexpr int kStages = I8sCfg<SUBS>::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_q = smem;                                   // 2 x 36 KB: sub-tile a | sub-tile b of the item (18 chunks each)
-  uint8_t* s_t = smem + 2 * kI8sQTileBytes;              // kI8Stages x 34 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_t + kI8Stages * kI8TileBytes + kI8ChunkBytes);  // +1 chunk: see below
+  uint8_t* s_q = smem;                                   // SUBS x 36 KB: the item's query sub-tiles (18 chunks each)
+  uint8_t* s_t = smem + SUBS * kI8sQTileBytes;           // kStages x 34 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_t + kStages * kI8TileBytes + kI8ChunkBytes);  // +1 chunk: see below
   uint64_t* b_go = bars;                                 // [kI8sGo]
-  uint64_t* b_empty = bars + kI8sGo;                     // [kI8Stages]
-  uint64_t* b_tfull = bars + kI8sGo + kI8Stages;         // [4] one per TMEM stage
-  uint64_t* b_qempty = bars + kI8sGo + kI8Stages + 4;    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kI8sGo + kI8Stages + 6);
-  uint2* s_merge = reinterpret_cast<uint2*>(s_tmem + 4);  // [2 item parities][2 sub-tiles][128]: the two sets of a sub-tile meet here
-  uint4* s_cur = reinterpret_cast<uint4*>(s_merge + 4 * kI8Tile);  // [16 epilogue warps][32 lanes]: staged bwd_best values (16x256b epilogue)
+  uint64_t* b_empty = bars + kI8sGo;                     // [4] (kStages used)
+  uint64_t* b_tfull = bars + kI8sGo + 4;                 // [4] one per TMEM stage
+  uint64_t* b_qempty = bars + kI8sGo + 8;                // [4] (SUBS used)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kI8sGo + 12);
+  uint2* s_merge = reinterpret_cast<uint2*>(s_tmem + 4);  // SUBS == 2 only: [2 item parities][2 sub-tiles][128], the two sets of a sub-tile meet here
+  uint4* s_cur = reinterpret_cast<uint4*>(s_merge + (SUBS == 2 ? 4 * kI8Tile : 0));  // [16 epilogue warps][32 lanes]: staged bwd_best values (16x256b epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_blocks = (p.q_tiles + 1) >> 1;
-  const int n_items = p.n_pairs * q_blocks;
+  const int q_blocks = (p.q_tiles + SUBS - 1) / SUBS;
+  const int t_split = p.t_split;
+  const int n_items = p.n_pairs * q_blocks * t_split;    // item w = ((pair * q_blocks) + qb) * t_split + part
 
   // the index K-step reads one chunk past the last ring slot (times the query tile's zero chunk):
   // keep that chunk inside the allocation and defined
   for (int i = threadIdx.x; i < kI8Tile; i += kI8sThreads) {
-    reinterpret_cast<uint4*>(s_t + kI8Stages * kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(s_t + kStages * kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (EPI == 1) {  // unified tiles: the query slots' chunk 17 is never loaded and must read as zero
-      reinterpret_cast<uint4*>(s_q + kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
-      reinterpret_cast<uint4*>(s_q + kI8sQTileBytes + kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int sub = 0; sub < SUBS; ++sub)
+        reinterpret_cast<uint4*>(s_q + sub * kI8sQTileBytes + kI8TileBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < kI8sGo; ++k) mbar_init(&b_go[k], 5);  // producer + the 4 warps that drained tile pair g-4
-    for (int s = 0; s < kI8Stages; ++s) mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&b_empty[s], 1);
     for (int a = 0; a < 4; ++a) {
       mbar_init(&b_tfull[a], 1);
       for (int k = 0; k < 4; ++k) mbar_arrive(&b_go[a]);  // tile pairs 0..3 find their TMEM stage free
     }
-    for (int a = 0; a < 2; ++a) mbar_init(&b_qempty[a], 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&b_qempty[a], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -698,21 +718,25 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  // all roles walk the same items; an item always has 2 * n_tt tile pairs (sub-tile b may be
-  // all padding: its MMAs then read stale shared memory and every result is ignored)
+  // all roles walk the same items; an item always has SUBS * (t1 - t0) tile pairs (trailing sub-tiles may
+  // be all padding: their MMAs then read stale shared memory and every result is ignored)
+#define B2S_I8S_ITEM(w)                                                                          \
+  const int part = (w) % t_split, pq = (w) / t_split;                                            \
+  const int pair = pq / q_blocks, qb = pq - pair * q_blocks;                                     \
+  const int nq = p.q_off[pair + 1] - p.q_off[pair];                                              \
+  const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;                                     \
+  const int n_tt = (nt + kI8Tile - 1) / kI8Tile;                                                 \
+  const int t0 = (int)(((long long)part * n_tt) / t_split), t1 = (int)(((long long)(part + 1) * n_tt) / t_split); \
+  if (qb * SUBS * kI8Tile >= nq || t0 >= t1) continue;
   if (warp == 0) {
     // ===== producer =====
     if (lane == 0) {
       uint32_t n = 0, tau = 0;  // items / train tiles seen by this CTA
       long long w_empty = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const int pair = w / q_blocks, qb = w - pair * q_blocks;
-        const int nq = p.q_off[pair + 1] - p.q_off[pair];
-        const int nt = p.t_off[pair + 1] - p.t_off[pair];
-        const int q0 = qb * 2 * kI8Tile;
-        if (q0 >= nq || nt == 0) continue;
-        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
-        const bool has_b = q0 + kI8Tile < nq;
+        B2S_I8S_ITEM(w)
+        (void)to;
+        const int q0 = qb * SUBS * kI8Tile;
         // EPI 1: unified 18-chunk tiles on both sides; a train slot takes chunks 0..16 (data + its B-side
         // index chunk, one copy), a query slot chunks 0..15 and chunk 17 (its A-side index chunk, two copies
         // once per item)
@@ -721,41 +745,35 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         const size_t t_tile0 = p.t_xt ? (size_t)p.t_xt[pair] : (size_t)pair * p.t_tiles;
         const size_t q_tile0 = p.q_xt ? (size_t)p.q_xt[pair] : (size_t)pair * p.q_tiles;
         const uint8_t* tsrc = p.tx + t_tile0 * kTStride;
-        const uint8_t* qsrc = p.qx + (q_tile0 + 2 * qb) * kI8sQTileBytes;
-        for (int t = 0; t < n_tt; ++t, ++tau) {
-          const uint32_t s = tau % kI8Stages, g = 2u * tau;
-          uint64_t* go_a = &b_go[g % kI8sGo];
-          uint64_t* go_b = &b_go[(g + 1u) % kI8sGo];
+        const uint8_t* qsrc = p.qx + (q_tile0 + (size_t)SUBS * qb) * kI8sQTileBytes;
+        for (int t = t0; t < t1; ++t, ++tau) {
+          const uint32_t s = tau % kStages, g = (uint32_t)SUBS * tau;
           const long long c0 = p.dbg ? clock64() : 0;
-          if (tau >= kI8Stages) mbar_wait_bounded(&b_empty[s], ((tau / kI8Stages) - 1u) & 1u);
+          if (tau >= (uint32_t)kStages) mbar_wait_bounded(&b_empty[s], ((tau / kStages) - 1u) & 1u);
           if (p.dbg) w_empty += clock64() - c0;
-          const bool skip_t = (p.mode & 2) && tau >= kI8Stages;
-          if (t == 0) {
-            if (n >= 1) mbar_wait_bounded(&b_qempty[0], (n - 1u) & 1u);
-            mbar_arrive_expect_tx(go_a, kQBytes + (skip_t ? 0 : kI8TileBytes));
-            if (EPI == 1) {
-              bulk_g2s(s_q, qsrc, 16 * kI8ChunkBytes, go_a);
-              bulk_g2s(s_q + 16 * kI8ChunkBytes, qsrc + 17 * kI8ChunkBytes, kI8ChunkBytes, go_a);
+          const bool skip_t = (p.mode & 2) && tau >= (uint32_t)kStages;
+#pragma unroll
+          for (int sub = 0; sub < SUBS; ++sub) {
+            uint64_t* go = &b_go[(g + (uint32_t)sub) % kI8sGo];
+            const bool load_q = t == t0 && q0 + sub * kI8Tile < nq;   // the item's query sub-tile rides on its first tile pair
+            const uint32_t t_bytes = (sub == 0 && !skip_t) ? (uint32_t)kI8TileBytes : 0u;
+            if (load_q) {
+              if (n >= 1) mbar_wait_bounded(&b_qempty[sub], (n - 1u) & 1u);
+              mbar_arrive_expect_tx(go, kQBytes + t_bytes);
+              uint8_t* qdst = s_q + sub * kI8sQTileBytes;
+              const uint8_t* qs = qsrc + (size_t)sub * kI8sQTileBytes;
+              if (EPI == 1) {
+                bulk_g2s(qdst, qs, 16 * kI8ChunkBytes, go);
+                bulk_g2s(qdst + 16 * kI8ChunkBytes, qs + 17 * kI8ChunkBytes, kI8ChunkBytes, go);
+              } else {
+                bulk_g2s(qdst, qs, kQBytes, go);
+              }
+            } else if (t_bytes) {
+              mbar_arrive_expect_tx(go, t_bytes);
             } else {
-              bulk_g2s(s_q, qsrc, kQBytes, go_a);
+              mbar_arrive(go);
             }
-          } else if (skip_t) {
-            mbar_arrive(go_a);
-          } else {
-            mbar_arrive_expect_tx(go_a, kI8TileBytes);
-          }
-          if (!skip_t) bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kTStride, kI8TileBytes, go_a);
-          if (t == 0 && has_b) {
-            if (n >= 1) mbar_wait_bounded(&b_qempty[1], (n - 1u) & 1u);
-            mbar_arrive_expect_tx(go_b, kQBytes);
-            if (EPI == 1) {
-              bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, 16 * kI8ChunkBytes, go_b);
-              bulk_g2s(s_q + kI8sQTileBytes + 16 * kI8ChunkBytes, qsrc + kI8sQTileBytes + 17 * kI8ChunkBytes, kI8ChunkBytes, go_b);
-            } else {
-              bulk_g2s(s_q + kI8sQTileBytes, qsrc + kI8sQTileBytes, kQBytes, go_b);
-            }
-          } else {
-            mbar_arrive(go_b);
+            if (t_bytes) bulk_g2s(s_t + (size_t)s * kI8TileBytes, tsrc + (size_t)t * kTStride, kI8TileBytes, go);
           }
         }
         ++n;
@@ -769,19 +787,17 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
       bool probed = false;
       long long w_full = 0;
       const long long t_start = p.dbg ? clock64() : 0;
-      const uint64_t qdesc_a = make_smem_desc(smem_u32(s_q));
-      const uint64_t qdesc_b = make_smem_desc(smem_u32(s_q + kI8sQTileBytes));
+      uint64_t qdesc[SUBS];
+#pragma unroll
+      for (int sub = 0; sub < SUBS; ++sub) qdesc[sub] = make_smem_desc(smem_u32(s_q + sub * kI8sQTileBytes));
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const int pair = w / q_blocks, qb = w - pair * q_blocks;
-        const int nq = p.q_off[pair + 1] - p.q_off[pair];
-        const int nt = p.t_off[pair + 1] - p.t_off[pair];
-        if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
-        const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
-        for (int t = 0; t < n_tt; ++t) {
-          const uint32_t s = (g >> 1) % kI8Stages;
+        B2S_I8S_ITEM(w)
+        (void)to;
+        for (int t = t0; t < t1; ++t) {
+          const uint32_t s = (g / (uint32_t)SUBS) % kStages;
           const uint64_t tdesc = make_smem_desc(smem_u32(s_t + (size_t)s * kI8TileBytes));
 #pragma unroll
-          for (uint32_t sub = 0; sub < 2; ++sub, ++g) {
+          for (uint32_t sub = 0; sub < (uint32_t)SUBS; ++sub, ++g) {
             if (!probed) {  // first tile pair, item boundaries, late epilogue or late loads
               const long long c0 = p.dbg ? clock64() : 0;
               mbar_wait_bounded(&b_go[g % kI8sGo], (g / kI8sGo) & 1u);
@@ -789,12 +805,12 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
             }
             tc_fence_after();
             const uint32_t gn = g + 1u;
-            const uint32_t more = (sub == 0 || t + 1 < n_tt) ? 1u : 0u;
-            probed = tc_mma_tile_single(tmem_base + (g & 3u) * 128u, sub ? qdesc_b : qdesc_a, tdesc, kIdescI8,
+            const uint32_t more = (sub + 1u < (uint32_t)SUBS || t + 1 < t1) ? 1u : 0u;
+            probed = tc_mma_tile_single(tmem_base + (g & 3u) * 128u, qdesc[sub], tdesc, kIdescI8,
                                         &b_go[gn % kI8sGo], (gn / kI8sGo) & 1u, more) != 0u;
-            if (sub == 1) tc_commit(&b_empty[s]);          // train tile consumed by both sub-tiles
+            if (sub == (uint32_t)SUBS - 1u) tc_commit(&b_empty[s]);  // train tile consumed by every sub-tile
             tc_commit(&b_tfull[g & 3u]);                    // accumulator stage complete
-            if (t == n_tt - 1) tc_commit(&b_qempty[sub]);   // the item's last use of this query sub-tile
+            if (t == t1 - 1) tc_commit(&b_qempty[sub]);     // the item's last use of this query sub-tile
           }
         }
       }
@@ -820,16 +836,13 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
     long long w_tfull = 0;
     const long long e_start = p.dbg ? clock64() : 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int pair = w / q_blocks, qb = w - pair * q_blocks;
-      const int qo = p.q_off[pair], nq = p.q_off[pair + 1] - qo;
-      const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
+      B2S_I8S_ITEM(w)
+      const int qo = p.q_off[pair];
       const int q0 = qb * 2 * kI8Tile + (int)sub * kI8Tile;   // first query row of this set's sub-tile
-      if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
-      const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
       const int rows_valid = max(0, min(kI8Tile, nq - q0));
       uint32_t gbest = kNone, gsecond = kNone;
-      for (int t = 0; t < n_tt; ++t) {
-        const uint32_t g = g_item + 2u * (uint32_t)t + sub;
+      for (int t = t0; t < t1; ++t) {
+        const uint32_t g = g_item + 2u * (uint32_t)(t - t0) + sub;
         if ((g & 3u) != set) continue;
         const int tbase = t * kI8Tile;
         const int nt_valid = min(kI8Tile, nt - tbase);
@@ -909,7 +922,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           if (rows_valid > 0 && cm16[k] < kKey16Valid && key < cur[k]) atomicMin(&p.bwd_best[to + tbase + 4 * lane + k], key);
         }
       }
-      g_item += 2u * (uint32_t)n_tt;
+      g_item += 2u * (uint32_t)(t1 - t0);
       // the two sets of a sub-tile (even / odd train tiles) meet in shared memory; double buffered by
       // item parity, so one named barrier per item is enough
       uint2* mg = s_merge + (((n & 1u) * 2u + sub) << 7);
@@ -919,8 +932,13 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
         const uint2 o = mg[row];
         top2_insert(gbest, gsecond, o.x);
         top2_insert(gbest, gsecond, o.y);
-        p.fwd_best[qo + q0 + row] = gbest >= kKey32Pad ? kNone : gbest;
-        p.fwd_second[qo + q0 + row] = gsecond >= kKey32Pad ? kNone : gsecond;
+        const uint32_t ob = gbest >= kKey32Pad ? kNone : gbest, os = gsecond >= kKey32Pad ? kNone : gsecond;
+        if (t_split > 1) {
+          p.partial[(size_t)part * p.total_nq + qo + q0 + row] = make_uint2(ob, os);
+        } else {
+          p.fwd_best[qo + q0 + row] = ob;
+          p.fwd_second[qo + q0 + row] = os;
+        }
       }
       ++n;
     }
@@ -943,7 +961,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
     //    level) and lane%4 = k finishes row k: one running top-2 per thread, as in the 32x32b form. =====
     const int quarter = warp & 3;
     const uint32_t set = (uint32_t)(warp - 2) >> 2;
-    const uint32_t sub = set & 1u;
+    const uint32_t sub = SUBS == 4 ? set : (set & 1u);
     const int gr = lane >> 2, tc = lane & 3;
     const int row = quarter * 32 + gr + 8 * tc;   // the tile-local row this lane keeps the running top-2 of
     const uint32_t row_base = (uint32_t)(quarter * 32 + gr);
@@ -953,18 +971,17 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
     long long w_tfull = 0;
     const long long e_start = DBG ? clock64() : 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int pair = w / q_blocks, qb = w - pair * q_blocks;
-      const int nq = p.q_off[pair + 1] - p.q_off[pair];
-      const int to = p.t_off[pair], nt = p.t_off[pair + 1] - to;
-      const int q0 = qb * 2 * kI8Tile + (int)sub * kI8Tile;
-      if (qb * 2 * kI8Tile >= nq || nt == 0) continue;
-      const int n_tt = (nt + kI8Tile - 1) / kI8Tile;
+      B2S_I8S_ITEM(w)
+      const int q0 = qb * SUBS * kI8Tile + (int)sub * kI8Tile;
       const int rows_valid = max(0, min(kI8Tile, nq - q0));
       const bool staged = (reinterpret_cast<uintptr_t>(p.bwd_best + to) & 15u) == 0;   // cp.async.cg moves 16 aligned bytes
       uint32_t gbest = kNone, gsecond = kNone;
-      // this set's tile pairs: g = g_item + 2 t + sub with g % 4 == set, i.e. every other train tile
-      for (int t = (int)(((set >> 1) ^ (g_item >> 1)) & 1u); t < n_tt; t += 2) {
-        const uint32_t g = g_item + 2u * (uint32_t)t + sub;
+      // this set's tile pairs: g = g_item + SUBS k + sub (k = t - t0) with g % 4 == set: every train tile of
+      // sub-tile `set` (SUBS == 4), every other train tile of sub-tile set & 1 (SUBS == 2)
+      constexpr int kStep = SUBS == 4 ? 1 : 2;
+      for (int k = SUBS == 4 ? 0 : (int)(((set >> 1) ^ (g_item >> 1)) & 1u); k < t1 - t0; k += kStep) {
+        const int t = t0 + k;
+        const uint32_t g = g_item + (uint32_t)SUBS * (uint32_t)k + sub;
         const int tbase = t * kI8Tile;
         // current column minima of this lane's 4 train rows (stale is fine: only used to skip atomics).
         // Holding them in registers through the top-2 costs more than it saves (96 registers, 64 of them
@@ -1098,19 +1115,30 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
           if (rows_valid > 0 && cm16[k] < kKey16Valid && key < cur[k]) atomicMin(&p.bwd_best[to + tbase + 4 * lane + k], key);
         }
       }
-      g_item += 2u * (uint32_t)n_tt;
-      // the two sets of a sub-tile (even / odd train tiles) meet in shared memory; double buffered by
-      // item parity, so one named barrier per item is enough
-      uint2* mg = s_merge + (((n & 1u) * 2u + sub) << 7);
-      if (set >= 2u) mg[row] = make_uint2(gbest, gsecond);
-      asm volatile("bar.sync %0, 256;" ::"r"(1u + sub) : "memory");
-      if (set < 2u && row < rows_valid) {
-        const uint2 o = mg[row];
-        top2_insert(gbest, gsecond, o.x);
-        top2_insert(gbest, gsecond, o.y);
+      g_item += (uint32_t)SUBS * (uint32_t)(t1 - t0);
+      bool writer = row < rows_valid;
+      if (SUBS == 2) {
+        // the two sets of a sub-tile (even / odd train tiles) meet in shared memory; double buffered by
+        // item parity, so one named barrier per item is enough
+        uint2* mg = s_merge + (((n & 1u) * 2u + sub) << 7);
+        if (set >= 2u) mg[row] = make_uint2(gbest, gsecond);
+        asm volatile("bar.sync %0, 256;" ::"r"(1u + sub) : "memory");
+        writer = writer && set < 2u;
+        if (writer) {
+          const uint2 o = mg[row];
+          top2_insert(gbest, gsecond, o.x);
+          top2_insert(gbest, gsecond, o.y);
+        }
+      }
+      if (writer) {
         const int qo = p.q_off[pair];
-        p.fwd_best[qo + q0 + row] = gbest >= kKey32Pad ? kNone : gbest;
-        p.fwd_second[qo + q0 + row] = gsecond >= kKey32Pad ? kNone : gsecond;
+        const uint32_t ob = gbest >= kKey32Pad ? kNone : gbest, os = gsecond >= kKey32Pad ? kNone : gsecond;
+        if (t_split > 1) {
+          p.partial[(size_t)part * p.total_nq + qo + q0 + row] = make_uint2(ob, os);
+        } else {
+          p.fwd_best[qo + q0 + row] = ob;
+          p.fwd_second[qo + q0 + row] = os;
+        }
       }
       ++n;
     }
@@ -1121,6 +1149,7 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
     }
   }
 
+#undef B2S_I8S_ITEM
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1289,13 +1318,53 @@ void hamming_i8_set_debug(unsigned long long* dev_buf, int mode) {
 constexpr size_t kI8SmemBytes =
     (size_t)(2 + kI8Stages) * kI8TileBytes + 2 * kI8ChunkBytes + 8 * (2 * kI8Stages + 9) + 128 * sizeof(uint2);
 
-constexpr size_t kI8sSmemBytes = 2 * (size_t)kI8sQTileBytes + (size_t)kI8Stages * kI8TileBytes + kI8ChunkBytes +
-                                 8 * (kI8sGo + kI8Stages + 6) + 16 + 4 * kI8Tile * sizeof(uint2) +
-                                 16 * 32 * sizeof(uint4);  // + the epilogue warps' staging slots for the current column minima
+int hamming_merge_launch(const uint2* partial, int total_nq, int t_split, uint32_t* fwd_best, uint32_t* fwd_second,
+                         cudaStream_t st);  // hamming_popc.cu
 
-size_t hamming_i8_workspace_bytes(int n_pairs, int max_nq, int max_nt) {
+// Work decomposition of the single-product kernel: sub-tiles per item and the train-axis split.
+// A lone 10 000 x 10 000 pair has 40 (pair, 256-query block) items for 148 SMs, a lone 2000 x 2000 pair 8:
+// the train axis is then cut into t_split pieces (merged afterwards on the packed keys, like K1's t_split) so
+// that whole waves of items cover the machine.
+struct I8sPlan {
+  int subs, t_split;
+};
+static I8sPlan plan_i8s(int n_pairs, int max_nq, int max_nt, int t_split_req, int mode) {
+  const int qt = (max_nq + kI8Tile - 1) / kI8Tile, tt = (max_nt + kI8Tile - 1) / kI8Tile;
+  const long sms = sm_count();
+  // 4 sub-tiles per item halve the L2 -> SM operand traffic but measured 8 % SLOWER on every BASELINE shape
+  // (0.276 vs 0.254 ms on the 296-pair batch, profiles/r02_k2s_plans.txt): the kernel is bound by the epilogue's
+  // ALU work, not by L2, and the 2-stage train ring prefetches less.  Kept selectable (mode bit 64) for A/B runs.
+  const int subs = ((mode & 64) && !(mode & 16)) ? 4 : 2;
+  const long base = (long)n_pairs * ((qt + subs - 1) / subs);
+  int ts = 1;
+  if (t_split_req > 0) {
+    ts = t_split_req;
+  } else if (base > 0 && base < 4 * sms) {
+    // waves x (train tiles per item + ~2 tiles of query loads and pipeline fill per item), smallest wins
+    long best_cost = -1;
+    for (int c = 1; c <= tt && c <= 64; ++c) {
+      const long waves = (base * c + sms - 1) / sms;
+      const long cost = waves * ((tt + c - 1) / c + 2);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        ts = c;
+      }
+    }
+  }
+  if (ts > tt) ts = tt;
+  if (ts < 1) ts = 1;
+  return I8sPlan{subs, ts};
+}
+
+static size_t partial_bytes(int total_nq, int t_split) {
+  return t_split > 1 ? (((size_t)total_nq * t_split * sizeof(uint2) + 127) & ~(size_t)127) : 0;
+}
+
+size_t hamming_i8_workspace_bytes(int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
   const size_t qt = (size_t)((max_nq + kI8Tile - 1) / kI8Tile), tt = (size_t)((max_nt + kI8Tile - 1) / kI8Tile);
-  return (size_t)n_pairs * (qt + tt) * kI8sQTileBytes;  // sized for the largest layout (unified 18-chunk tiles on both sides)
+  const I8sPlan pl = plan_i8s(n_pairs, max_nq, max_nt, t_split, 0);
+  // sized for the largest layout (unified 18-chunk tiles on both sides) + the partial top-2 of a train-axis split
+  return (size_t)n_pairs * (qt + tt) * kI8sQTileBytes + partial_bytes(total_nq, pl.t_split);
 }
 
 // every key starts as "none".  Three separate memset nodes on purpose: ONE 7 MB memset over the (often
@@ -1311,15 +1380,57 @@ static int clear_keys(uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_be
   return B2S_OK;
 }
 
+// the single-product kernel: picks the instantiation, opts into its shared memory (per launch: the
+// attribute is per device, and a process may drive several), brackets it with the timing events
+template <int EPI, bool DBG, int SUBS>
+static int launch_i8s_inst(const I8Params& p, int grid, cudaStream_t st) {
+  static bool attr_set[64] = {false};   // one flag array per instantiation
+  if (first_use_on_device(attr_set))
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<EPI, DBG, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)I8sCfg<SUBS>::kSmem));
+  hamming_knn2_i8s_kernel<EPI, DBG, SUBS><<<grid, kI8sThreads, I8sCfg<SUBS>::kSmem, st>>>(p);
+  return B2S_OK;
+}
+static int g_i8_last_plan[3] = {0, 0, 0};   // subs, t_split, grid of the most recent launch (diagnostics)
+void hamming_i8_last_plan(int* subs, int* t_split, int* grid) {
+  if (subs) *subs = g_i8_last_plan[0];
+  if (t_split) *t_split = g_i8_last_plan[1];
+  if (grid) *grid = g_i8_last_plan[2];
+}
+static int launch_i8s(I8Params& p, const I8sPlan& pl, int total_nq, uint8_t* partial_ws, cudaStream_t st) {
+  p.t_split = pl.t_split;
+  p.total_nq = total_nq;
+  p.partial = pl.t_split > 1 ? reinterpret_cast<uint2*>(partial_ws) : nullptr;
+  if (pl.t_split > 1)   // parts that own no train tile of a short pair still report "none"
+    B2S_CUDA(cudaMemsetAsync(partial_ws, 0xFF, sizeof(uint2) * (size_t)total_nq * pl.t_split, st));
+  const long items = (long)((p.q_tiles + pl.subs - 1) / pl.subs) * p.n_pairs * pl.t_split;
+  const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
+  g_i8_last_plan[0] = pl.subs, g_i8_last_plan[1] = pl.t_split, g_i8_last_plan[2] = grid;
+  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
+  int rc;
+  if (p.mode & 16) rc = launch_i8s_inst<0, true, 2>(p, grid, st);            // 32x32b epilogue (A/B partner)
+  else if (pl.subs == 4) rc = p.dbg ? launch_i8s_inst<1, true, 4>(p, grid, st) : launch_i8s_inst<1, false, 4>(p, grid, st);
+  else rc = p.dbg ? launch_i8s_inst<1, true, 2>(p, grid, st) : launch_i8s_inst<1, false, 2>(p, grid, st);
+  if (rc) return rc;
+  B2S_CUDA(cudaGetLastError());
+  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
+  note_launch();
+  if (pl.t_split > 1) return hamming_merge_launch(p.partial, total_nq, pl.t_split, p.fwd_best, p.fwd_second, st);
+  return B2S_OK;
+}
+
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
-                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, void* workspace,
-                      size_t workspace_bytes, int single, cudaStream_t st) {
+                      int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, int t_split,
+                      void* workspace, size_t workspace_bytes, int single, cudaStream_t st) {
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;  // rows of pairs without train descriptors keep "none"
   if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0) return B2S_OK;
   const int qt = (max_nq + kI8Tile - 1) / kI8Tile, tt = (max_nt + kI8Tile - 1) / kI8Tile;
-  const size_t need = hamming_i8_workspace_bytes(n_pairs, max_nq, max_nt);
+  const size_t tiles_bytes = (size_t)n_pairs * (qt + tt) * kI8sQTileBytes;
+  I8sPlan pl = plan_i8s(n_pairs, max_nq, max_nt, single ? t_split : 1, g_i8_mode);
+  while (pl.t_split > 1 && tiles_bytes + partial_bytes(total_nq, pl.t_split) > workspace_bytes) --pl.t_split;  // shrink rather than fail
+  const size_t need = tiles_bytes + partial_bytes(total_nq, single ? pl.t_split : 1);
   B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "i8 variant needs %zu workspace bytes (b2s_hamming_workspace_bytes_v), got %zu", need, workspace_bytes);
   B2S_REQUIRE(((uintptr_t)workspace & 127u) == 0, "workspace must be 128-byte aligned");
@@ -1334,12 +1445,6 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
                                                                                 reinterpret_cast<uint4*>(tx), nullptr, nullptr);
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kI8SmemBytes));
-    attr_set = true;
-  }
   I8Params p;
   p.qx = qx;
   p.tx = tx;
@@ -1355,28 +1460,13 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.t_xt = nullptr;
   p.dbg = g_i8_dbg;
   p.mode = g_i8_mode;
-  if (single) {
-    static bool attr_set1 = false;
-    if (!attr_set1) {
-      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kI8sSmemBytes));
-      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kI8sSmemBytes));
-      B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kI8sSmemBytes));
-      attr_set1 = true;
-    }
-    const long items = (long)((qt + 1) / 2) * n_pairs;
-    const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
-    if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
-    if (p.mode & 16) hamming_knn2_i8s_kernel<0, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);   // 32x32b epilogue (A/B partner)
-    else if (p.dbg) hamming_knn2_i8s_kernel<1, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);   // with the stall counters
-    else hamming_knn2_i8s_kernel<1, false><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
-    B2S_CUDA(cudaGetLastError());
-    if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
-    note_launch();
-    return B2S_OK;
-  }
+  p.t_split = 1;
+  p.total_nq = total_nq;
+  p.partial = nullptr;
+  if (single) return launch_i8s(p, pl, total_nq, static_cast<uint8_t*>(workspace) + tiles_bytes, st);
+  static bool attr_set[64] = {false};
+  if (first_use_on_device(attr_set))
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8SmemBytes));
   const long items = (long)qt * n_pairs;
   const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
   if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
@@ -1387,7 +1477,10 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   return B2S_OK;
 }
 
-size_t hamming_i8_shared_workspace_bytes(int total_tiles) { return (size_t)total_tiles * kI8sQTileBytes; }
+size_t hamming_i8_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
+  const I8sPlan pl = plan_i8s(n_pairs, max_nq, max_nt, t_split, 0);
+  return (size_t)total_tiles * kI8sQTileBytes + partial_bytes(total_nq, pl.t_split);
+}
 
 // Batches whose pairs share descriptor blocks (frames): every block is expanded ONCE into unified
 // tiles, the pairs address them through q_xtile / t_xtile.  Single-product kernel, 16x256b epilogue.
@@ -1395,12 +1488,15 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
                              const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                              const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                              int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                             uint32_t* fwd_second, uint32_t* bwd_best, void* workspace, size_t workspace_bytes,
-                             cudaStream_t st) {
+                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st) {
   B2S_REQUIRE(n_blocks <= 65535, "n_blocks %d exceeds grid.y limit 65535; split the batch", n_blocks);
   if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;
   if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0 || n_blocks == 0) return B2S_OK;
-  const size_t need = hamming_i8_shared_workspace_bytes(total_tiles);
+  const size_t tiles_bytes = (size_t)total_tiles * kI8sQTileBytes;
+  I8sPlan pl = plan_i8s(n_pairs, max_nq, max_nt, t_split, g_i8_mode & ~16);
+  while (pl.t_split > 1 && tiles_bytes + partial_bytes(total_nq, pl.t_split) > workspace_bytes) --pl.t_split;
+  const size_t need = tiles_bytes + partial_bytes(total_nq, pl.t_split);
   B2S_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "shared-block Hamming needs %zu workspace bytes (b2s_hamming_shared_workspace_bytes), got %zu", need,
               workspace_bytes);
@@ -1411,14 +1507,6 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
                                                        blk_rows, blk_tile0);
   B2S_CUDA(cudaGetLastError());
   note_launch();
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kI8sSmemBytes));
-    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kI8sSmemBytes));
-    attr_set = true;
-  }
   I8Params p;
   p.qx = x;
   p.tx = x;
@@ -1434,15 +1522,7 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
   p.t_xt = t_xtile;
   p.dbg = g_i8_dbg;
   p.mode = g_i8_mode & ~16;
-  const long items = (long)((p.q_tiles + 1) / 2) * n_pairs;
-  const int grid = (int)(items < (long)sm_count() ? items : (long)sm_count());
-  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
-  if (p.dbg) hamming_knn2_i8s_kernel<1, true><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
-  else hamming_knn2_i8s_kernel<1, false><<<grid, kI8sThreads, kI8sSmemBytes, st>>>(p);
-  B2S_CUDA(cudaGetLastError());
-  if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
-  note_launch();
-  return B2S_OK;
+  return launch_i8s(p, pl, total_nq, x + tiles_bytes, st);
 }
 
 }  // namespace b2s

@@ -205,6 +205,15 @@ __global__ void hamming_merge_kernel(const uint2* __restrict__ partial, int tota
   fwd_second[i] = second;
 }
 
+int hamming_merge_launch(const uint2* partial, int total_nq, int t_split, uint32_t* fwd_best, uint32_t* fwd_second,
+                         cudaStream_t st) {   // also folds the train-axis split of the tensor-core kernel (hamming_i8.cu)
+  if (total_nq <= 0) return B2S_OK;
+  hamming_merge_kernel<<<(total_nq + 255) / 256, 256, 0, st>>>(partial, total_nq, t_split, fwd_best, fwd_second);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
+
 // ---- host side -----------------------------------------------------------------
 static int g_csa = 2, g_rows = 2, g_warps = 4;
 

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kHomThreads) homography_dlt_kernel(
   const int pair = blockIdx.y;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   double* ho = H_out + ((size_t)pair * H + h) * 9;
   int idx[4];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kHomThreads) homography_score_kernel(
   __shared__ P4 s_p[kHomChunk];
   const int pair = blockIdx.y;
   const int h = blockIdx.x * kHomThreads + threadIdx.x;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   const double th = th_pp ? th_pp[pair] : th_all;
   const bool live = h < H;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) homography_select_kernel(
   __shared__ unsigned long long s_best;
   __shared__ int s_cnt;
   const int pair = blockIdx.x, tid = threadIdx.x;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   if (tid == 0) {
     s_early = 0x7FFFFFFF;
     s_best = 0ull;

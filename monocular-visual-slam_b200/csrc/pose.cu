@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) cheirality_vote_kernel(const float4* __re
                                                               int32_t* __restrict__ votes) {
   const int pair = blockIdx.y;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const bool live = m < M && (mask == nullptr || mask[c_off[pair] + m] != 0);
   int in_front[4] = {0, 0, 0, 0};
   if (live) {
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kRefitThreads) refit_essential_kernel(
   __shared__ double s_cs[2];
   __shared__ int s_n[8];
   const int pair = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   const uint8_t* mp = mask ? mask + c_off[pair] : nullptr;
   double acc[45];

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
   __shared__ P4 s_p[kScoreChunk];
   const int pair = blockIdx.y;
   const int h = blockIdx.x * kScoreThreads + threadIdx.x;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   const T th2 = (T)(th2_pp ? th2_pp[pair] : th2_all);
   T e[9];
@@ -92,8 +92,19 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   __shared__ float s_w[2];
   const int pair = blockIdx.y;
   const int h = blockIdx.x * kScoreHThreads + threadIdx.x;
-  const int M = c_count[pair];
+  // gridDim.z > 1: the pair's correspondences are cut into gridDim.z slices (multiples of 32) and the counts
+  // are summed with atomicAdd into a zeroed array — a lone pair with thousands of correspondences (BASELINE
+  // config #4: 4096 hypotheses x ~7000 matches = 32 CTAs otherwise) then fills the machine.  The rounding bound
+  // only needs W1 / W2 >= the norms of the correspondences this CTA evaluates, so the slice's own maxima serve.
+  int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
+  if (gridDim.z > 1) {
+    const int per = (((M + (int)gridDim.z - 1) / (int)gridDim.z) + 31) & ~31;
+    const int lo = min(M, (int)blockIdx.z * per);
+    M = min(M, lo + per) - lo;
+    cp += lo;
+    if (M <= 0) return;   // uniform for the CTA
+  }
   const double th2d = th2_pp ? th2_pp[pair] : th2_all;
   const float th2 = (float)th2d;
   const bool live = h < H;
@@ -208,7 +219,10 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
       }
     }
   }
-  if (live) counts[(size_t)pair * H + h] = count;
+  if (live) {
+    if (gridDim.z > 1) atomicAdd(&counts[(size_t)pair * H + h], count);
+    else counts[(size_t)pair * H + h] = count;
+  }
 }
 
 // ---- winner selection + inlier mask ---------------------------------------------------
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
   __shared__ unsigned long long s_best;
   __shared__ int s_cnt;
   const int pair = blockIdx.x, tid = threadIdx.x;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   if (tid == 0) {
     s_early = 0x7FFFFFFF;
     s_best = 0ull;
@@ -280,18 +294,20 @@ template <bool AFFINE, bool KEYE>
 __global__ void __launch_bounds__(kEpThreads, 4) eight_point_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count, int H,
     const int32_t* __restrict__ samples_in, uint64_t seed, int32_t* __restrict__ samples_out, const Mat3 K,
-    const Mat3 Kinv, double* __restrict__ E_out) {
+    const Mat3 Kinv, double* __restrict__ E_out, const int32_t* __restrict__ pair_ids, int pair_id0) {
   const int pair = blockIdx.y;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
   double* eo = E_out + ((size_t)pair * H + h) * 9;
   int idx[8];
   if (samples_in) {
     for (int k = 0; k < 8; ++k) idx[k] = samples_in[((size_t)pair * H + h) * 8 + k];
   } else if (M >= 8) {
-    draw_distinct<8>(seed, pair, h, M, idx);
+    // the stream is keyed by the pair's GLOBAL id, so a pair draws the same samples whichever rank / batch
+    // position it is processed at (pair-sharded runs equal the single-GPU run bit for bit)
+    draw_distinct<8>(seed, pair_ids ? pair_ids[pair] : pair_id0 + pair, h, M, idx);
   } else {
     for (int k = 0; k < 8; ++k) idx[k] = 0;
   }
@@ -368,8 +384,9 @@ int ransac_score_fp64_cond_launch(const float4* corr, const int32_t* c_off, cons
 extern "C" {
 
 int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, int H,
-                            const int32_t* samples_in, uint64_t seed, int32_t* samples_out, const double* K_host,
-                            const double* Kinv_host, double* E_out, void* stream) {
+                            const int32_t* samples_in, uint64_t seed, const int32_t* pair_ids, int pair_id0,
+                            int32_t* samples_out, const double* K_host, const double* Kinv_host, double* E_out,
+                            void* stream) {
   using namespace b2s;
   B2S_REQUIRE(corr && c_off && c_count && E_out, "null pointer");
   B2S_REQUIRE(n_pairs >= 0 && H >= 0, "negative size");
@@ -388,7 +405,7 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* c4 = reinterpret_cast<const float4*>(corr);
 #define B2S_EP_LAUNCH(A_, K_) \
-  eight_point_kernel<A_, K_><<<grid, kEpThreads, 0, st>>>(c4, c_off, c_count, H, samples_in, seed, samples_out, K, Kinv, E_out)
+  eight_point_kernel<A_, K_><<<grid, kEpThreads, 0, st>>>(c4, c_off, c_count, H, samples_in, seed, samples_out, K, Kinv, E_out, pair_ids, pair_id0)
   if (affine && keye) B2S_EP_LAUNCH(true, true);
   else if (affine) B2S_EP_LAUNCH(true, false);
   else B2S_EP_LAUNCH(false, false);
@@ -400,7 +417,7 @@ int b2s_eight_point_batched(const float* corr, const int32_t* c_off, const int32
 
 int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs,
                              const double* E, int H, double th2, const double* th2_per_pair, int precision,
-                             int32_t* counts, void* stream) {
+                             int max_m, int32_t* counts, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(corr && c_off && c_count && E && counts, "null pointer");
   B2S_REQUIRE(precision == 64 || precision == 32 || precision == 6464, "precision must be 64, 32 or 6464");
@@ -410,9 +427,20 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
   dim3 grid((H + kScoreThreads - 1) / kScoreThreads, n_pairs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* c4 = reinterpret_cast<const float4*>(corr);
-  if (precision == 64)
+  if (precision == 64) {
+    // few pairs with many correspondences each: slice the correspondences too (see the kernel)
+    const long blocks = (long)grid.x * grid.y, sms = sm_count();
+    int zs = 1;
+    if (max_m > 2 * kScoreHChunk && blocks < sms) {
+      const long want = (2 * sms + blocks - 1) / blocks, most = (max_m + kScoreHChunk - 1) / kScoreHChunk;
+      zs = (int)(want < most ? want : most);
+    }
+    if (zs > 1) {
+      B2S_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * H, st));
+      grid.z = zs;
+    }
     ransac_score_hybrid_kernel<<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
-  else if (precision == 6464)
+  } else if (precision == 6464)
     ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
   else
     ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);

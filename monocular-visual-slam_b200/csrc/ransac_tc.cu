@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) tc_prep_corr_kernel(const float4* __restr
                                                            uint4* __restrict__ out, int* __restrict__ pairmax) {
   const int pair = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int m = tile * kTcTileRows + r;
-  const int M = c_count[pair];
+  const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   if (tile * kTcTileRows >= M) return;  // tile never read
   float hi[32], lo[32];
 #pragma unroll
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ransac_score_tc_kernel(const Tc
       uint32_t n = 0, g = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int pair = w / p.h_tiles, ht = w - pair * p.h_tiles;
-        const int M = p.c_count[pair];
+        const int M = max(p.c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
         if (M <= 0 || ht * kTcTileRows >= p.H) continue;
         const int n_mt = (M + kTcTileRows - 1) / kTcTileRows;
         const uint32_t ab = n & 1u;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ransac_score_tc_kernel(const Tc
       bool probed = false;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int pair = w / p.h_tiles, ht = w - pair * p.h_tiles;
-        const int M = p.c_count[pair];
+        const int M = max(p.c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
         if (M <= 0 || ht * kTcTileRows >= p.H) continue;
         const int n_mt = (M + kTcTileRows - 1) / kTcTileRows;
         const uint32_t ab = n & 1u;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ransac_score_tc_kernel(const Tc
     int wl_at = 0, wl_end = 0;  // this warp's reserved slice of the work list (uniform across the warp)
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int pair = w / p.h_tiles, ht = w - pair * p.h_tiles;
-      const int M = p.c_count[pair];
+      const int M = max(p.c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
       if (M <= 0 || ht * kTcTileRows >= p.H) continue;
       const int n_mt = (M + kTcTileRows - 1) / kTcTileRows;
       const int h = ht * kTcTileRows + row;
@@ -535,11 +535,9 @@ int b2s_ransac_score_tc(const float* corr, const int32_t* c_off, const int32_t* 
                                                          reinterpret_cast<uint4*>(bx), pairmax);
   B2S_CUDA(cudaGetLastError());
   note_launch(2);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (first_use_on_device(attr_set))
     B2S_CUDA(cudaFuncSetAttribute(ransac_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    attr_set = true;
-  }
   TcParams p;
   p.ax = ax;
   p.bx = bx;

@@ -33,6 +33,7 @@ struct SelectParams {
   int32_t* __restrict__ out_d;
   float4* __restrict__ out_corr;
   int32_t* __restrict__ out_count;
+  int32_t* __restrict__ out_total;    // optional: survivors before truncation
   int use_ratio, use_cross, sort_by_distance, max_matches;
   int n_sort;  // power of two >= max_nq
 };
@@ -59,7 +60,10 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
   const int ob = p.out_stride > 0 ? pair * p.out_stride : qo;  // output base
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   if (nq > p.n_sort) {  // caller's max_nq was too small for this pair: flag it, never overrun smem
-    if (tid == 0) p.out_count[pair] = -1;
+    if (tid == 0) {
+      p.out_count[pair] = -1;
+      if (p.out_total) p.out_total[pair] = -1;
+    }
     return;
   }
   for (int b = tid; b < kSelBins + 31; b += nthr) s_hist[b] = 0;
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
   __syncthreads();
 
   int count = s_count;
+  if (tid == 0 && p.out_total) p.out_total[pair] = count;
   if (p.max_matches > 0 && count > p.max_matches) count = p.max_matches;
   if (p.out_stride > 0 && count > p.out_stride) {  // caller's stride cannot hold this pair: flag, never overrun
     if (tid == 0) p.out_count[pair] = -1;
@@ -158,7 +163,7 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
                                   int sort_by_distance, int max_matches, const float* kp_q, const float* kp_t,
                                   const int32_t* kp_q_src_row, const int32_t* kp_t_src_row, int out_stride,
                                   int32_t* out_q, int32_t* out_t, int32_t* out_d, float* out_corr,
-                                  int32_t* out_count, void* stream) {
+                                  int32_t* out_count, int32_t* out_total, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(n_pairs >= 0 && max_nq >= 0 && out_stride >= 0, "negative size");
   B2S_REQUIRE(max_nq <= B2S_SELECT_MAX_QUERIES, "select: %d queries per pair exceeds %d", max_nq,
@@ -190,6 +195,7 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
   p.out_d = out_d;
   p.out_corr = reinterpret_cast<float4*>(out_corr);
   p.out_count = out_count;
+  p.out_total = out_total;
   p.use_ratio = use_ratio;
   p.use_cross = use_cross;
   p.sort_by_distance = sort_by_distance;

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b2s.h but not exported"
     assert sorted(_capi.EXPORTS) == names
-    assert _capi.load_library().b2s_abi_version() == 1
+    assert _capi.load_library().b2s_abi_version() == _capi.ABI_VERSION
 
 
 def test_header_constants_agree_with_host_and_oracle():

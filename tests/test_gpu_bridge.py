@@ -172,9 +172,10 @@ def test_frontend_with_pose_recovers_the_planted_motion():
 
 
 def test_sequence_pipeline_equals_single_shot_frontend():
-    """SequencePipeline (three streams, depth 2, a CUDA graph per buffer set) returns, for every submitted
-    sequence, exactly what one Frontend.run on the same frames returns — also when the slots are reused
-    with different data, and eagerly (use_graph=False)."""
+    """SequencePipeline (depth 2; both schedules: whole-step graphs on per-slot streams, and three streams with
+    the kernels serialised) returns, for every submitted sequence, exactly what one Frontend.run on the same frames
+    returns — through the ONE packed record download per step — also when the slots are reused with different
+    data / host buffers, and eagerly (use_graph=False)."""
     import torch
     from b200slam.frontend import Frontend, FrontendConfig, SequencePipeline, sequence_batch
     from b200slam.synthetic import tracking_sequence
@@ -192,8 +193,8 @@ def test_sequence_pipeline_equals_single_shot_frontend():
                                                            ("out_q", r.sel.out_q), ("out_t", r.sel.out_t), ("out_d", r.sel.out_d),
                                                            ("mask", r.inlier_mask))})
     hosts = [(torch.from_numpy(d.reshape(-1, 32)).pin_memory(), torch.from_numpy(k.reshape(-1, 2)).pin_memory()) for d, k in seqs]
-    for use_graph in (True, False):
-        pipe = SequencePipeline(F, N, cfg, depth=2, use_graph=use_graph)
+    for use_graph, schedule in ((True, "interleaved"), (True, "serial"), (False, "serial"), (False, "interleaved")):
+        pipe = SequencePipeline(F, N, cfg, depth=2, use_graph=use_graph, schedule=schedule)
         order = [0, 1, 2, 1, 0, 2, 2]
         slots = []
         for i in order:                                       # submit everything first: slots are reused while in flight

@@ -99,3 +99,24 @@ def test_relocalize_end_to_end_finds_the_planted_keyframe():
     assert abs(float(res.translation @ t_true)) > 0.98                         # direction up to the usual sign / noise
     # nothing passes a match gate no keyframe can meet
     assert BatchedMapRelocalizer(snap, np.eye(3), score_threshold=0.0, max_candidates=5, min_matches=10_000).relocalize(kps, q_desc) is None
+
+
+def test_two_relocalizers_share_a_vocabulary_but_not_a_map():
+    """Two snapshots built on the SAME vocabulary (old and new map): each relocalizer scores against its
+    own histograms (the reference recomputes cosine_similarity against self.snapshot.bow_hists on every
+    call, persistent_map.py:234-235) even when their first queries interleave."""
+    from integration.relocalization_bridge import BatchedMapRelocalizer, host_bow_scores
+    rng = np.random.default_rng(31)
+    snap_a, _, q_desc, _ = _synthetic_map(rng, n_kf=30, n_desc=200)
+    snap_b, _, _, _ = _synthetic_map(rng, n_kf=26, n_desc=200)
+    snap_b = _Snap(snap_b.keyframes, snap_a.bow_vocab,
+                   np.vstack([host_bow_scores.__globals__["host_bow_histogram"](k.descriptors, snap_a.bow_vocab) for k in snap_b.keyframes]),
+                   snap_b.bow_frame_ids)
+    ra, rb = BatchedMapRelocalizer(snap_a, np.eye(3)), BatchedMapRelocalizer(snap_b, np.eye(3))
+    sa1 = ra._bow_scores(q_desc)
+    sb1 = rb._bow_scores(q_desc)
+    sa2 = ra._bow_scores(q_desc)          # after rb's first query: must still be map A
+    assert sa1.shape == (30,) and sb1.shape == (26,)
+    np.testing.assert_array_equal(sa1, sa2)
+    np.testing.assert_allclose(sa1, host_bow_scores(q_desc, snap_a.bow_vocab, snap_a.bow_hists), atol=2e-6)
+    np.testing.assert_allclose(sb1, host_bow_scores(q_desc, snap_b.bow_vocab, snap_b.bow_hists), atol=2e-6)

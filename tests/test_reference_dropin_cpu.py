@@ -29,6 +29,22 @@ def test_shim_resolves_and_importers_load():
     assert "homography.ransac_essential" in r.stdout and "persistent_map._build_matcher" in r.stdout
 
 
+def test_install_rebinds_importers_regardless_of_import_order():
+    """slam_api does `from persistent_map import MapRelocalizer` and `from keyframe_manager import
+    KeyframeManager` (slam_api.py:41-43): importing it BEFORE install() must still end on the device classes."""
+    r = _run("import slam_api, persistent_map, keyframe_manager;"
+             "from integration.pose_bridge import install; from integration.relocalization_bridge import BatchedMapRelocalizer;"
+             "p = install();"
+             "assert slam_api.MapRelocalizer is BatchedMapRelocalizer and persistent_map.MapRelocalizer is BatchedMapRelocalizer, p;"
+             "assert slam_api.KeyframeManager is keyframe_manager.KeyframeManager and slam_api.KeyframeManager._b2s_device_matcher;"
+             "km = slam_api.KeyframeManager(); assert km.matcher is not None;"
+             "km2 = slam_api.KeyframeManager(matcher=len); assert km2.matcher is len;"
+             "p2 = install(); assert sorted(p2) == sorted(p);"
+             "print(sorted(p)); print('skipped', install.skipped)")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "slam_api.MapRelocalizer" in r.stdout and "slam_api.KeyframeManager" in r.stdout
+
+
 @pytest.mark.parametrize("test_file", ["test_slam_api.py", "test_feature_control_plane.py", "test_tracking_control_plane.py"])
 def test_reference_tests_pass_with_the_bridge(test_file, tmp_path):
     env = dict(os.environ, PYTHONPATH=f"{ROOT}{os.pathsep}{REF}", PYTHONDONTWRITEBYTECODE="1")
