@@ -30,6 +30,31 @@ _ransac = None
 _ransac_pid = None
 _lock = threading.Lock()
 
+# Reference-stream mode (parity tests, deterministic replays): when set to a callable returning a
+# ``numpy.random.Generator``, every RANSAC drop-in called WITHOUT ``rng`` asks it for one — exactly where the
+# reference calls ``np.random.default_rng()`` (homography.py:191-192, 315-316) — and draws its minimal samples from
+# that generator's ``choice`` stream instead of the device RNG.  None (default) = device RNG, like production.
+RNG_FACTORY = None
+
+
+def _draw_reference_stream(rng, n: int, k: int, max_iter: int):
+    """``rng.choice(n, k, replace=False)`` per iteration, in order (homography.py:193 / :325) -> ((max_iter, k) int32,
+    the generator state before the first draw)."""
+    state = rng.bit_generator.state
+    out = np.zeros((max_iter, k), np.int32)
+    if n >= k:
+        for it in range(max_iter):
+            out[it] = rng.choice(n, k, replace=False)
+    return out, state
+
+
+def _rewind_to_reference_state(rng, state, n: int, k: int, draws: int):
+    """Leave the caller's generator where the reference's sequential loop leaves it: `draws` iterations consumed
+    (it stops at the first hypothesis above 0.8 n, homography.py:210-211 / :338-339)."""
+    rng.bit_generator.state = state
+    for _ in range(draws):
+        rng.choice(n, k, replace=False)
+
 
 def _device_ransac():
     global _ransac, _ransac_pid
@@ -94,13 +119,15 @@ def ransac_essential_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000,
     off_d = torch.from_numpy(off).to(dev)
     cnt_d = torch.from_numpy(counts_np).to(dev)
     samples_d = None
+    if rngs is None and RNG_FACTORY is not None:
+        rngs = [RNG_FACTORY() for _ in range(n_pairs)]
+    states = None
     if rngs is not None:
         smp = np.zeros((n_pairs, max_iter, 8), np.int32)
+        states = []
         for p, rng in enumerate(rngs):                               # homography.py:325, same stream
-            n = int(counts_np[p])
-            if n >= 8:
-                for it in range(max_iter):
-                    smp[p, it] = rng.choice(n, 8, replace=False)
+            smp[p], st = _draw_reference_stream(rng, int(counts_np[p]), 8, max_iter)
+            states.append(st)
         samples_d = torch.from_numpy(smp).to(dev)
     if seed is None:
         seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
@@ -109,7 +136,12 @@ def ransac_essential_batch(src_list, dst_list, K, th=0.01, max_iter: int = 2000,
     E = R.hypotheses(corr_d, off_d, cnt_d, n_pairs, max_iter, samples=samples_d, seed=seed, K=K)
     counts = R.score(corr_d, off_d, cnt_d, n_pairs, E, 0.0, th2_per_pair=th2_d, precision=64, max_m=int(counts_np.max()) if n_pairs else 0)
     best_h, best_c, mask = R.select(counts, corr_d, off_d, cnt_d, n_pairs, E, 0.0, th2_per_pair=th2_d)
-    best_h, mask = best_h.cpu().numpy(), mask.cpu().numpy()
+    best_h, best_c, mask = best_h.cpu().numpy(), best_c.cpu().numpy(), mask.cpu().numpy()
+    if states is not None:
+        for p, rng in enumerate(rngs):                               # the early exit consumed best_h + 1 draws only
+            n = int(counts_np[p])
+            if n >= 8 and best_h[p] >= 0 and best_c[p] > 0.8 * n:
+                _rewind_to_reference_state(rng, states[p], n, 8, int(best_h[p]) + 1)
     return [(int(best_h[p]), np.flatnonzero(mask[off[p]:off[p + 1]])) for p in range(n_pairs)]
 
 
@@ -148,13 +180,15 @@ def ransac_homography_batch(src_list, dst_list, th=3.0, max_iter: int = 2000, rn
     dev = torch.device("cuda", torch.cuda.current_device())
     corr_d, off_d, cnt_d = torch.from_numpy(corr).to(dev), torch.from_numpy(off).to(dev), torch.from_numpy(counts_np).to(dev)
     samples_d = None
+    if rngs is None and RNG_FACTORY is not None:
+        rngs = [RNG_FACTORY() for _ in range(n_pairs)]
+    states = None
     if rngs is not None:
         smp = np.zeros((n_pairs, max_iter, 4), np.int32)
+        states = []
         for p, rng in enumerate(rngs):                               # homography.py:193, same stream
-            n = int(counts_np[p])
-            if n >= 4:
-                for it in range(max_iter):
-                    smp[p, it] = rng.choice(n, 4, replace=False)
+            smp[p], st = _draw_reference_stream(rng, int(counts_np[p]), 4, max_iter)
+            states.append(st)
         samples_d = torch.from_numpy(smp).to(dev)
     if seed is None:
         seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
@@ -163,7 +197,12 @@ def ransac_homography_batch(src_list, dst_list, th=3.0, max_iter: int = 2000, rn
     Hm = R.hypotheses(corr_d, off_d, cnt_d, n_pairs, max_iter, samples=samples_d, seed=seed)
     counts = R.score(corr_d, off_d, cnt_d, n_pairs, Hm, 0.0, th_per_pair=th_d)
     best_h, best_c, mask = R.select(counts, corr_d, off_d, cnt_d, n_pairs, Hm, 0.0, th_per_pair=th_d)
-    best_h, mask = best_h.cpu().numpy(), mask.cpu().numpy()
+    best_h, best_c, mask = best_h.cpu().numpy(), best_c.cpu().numpy(), mask.cpu().numpy()
+    if states is not None:
+        for p, rng in enumerate(rngs):
+            n = int(counts_np[p])
+            if n >= 4 and best_h[p] >= 0 and best_c[p] > 0.8 * n:
+                _rewind_to_reference_state(rng, states[p], n, 4, int(best_h[p]) + 1)
     return [(int(best_h[p]), np.flatnonzero(mask[off[p]:off[p + 1]])) for p in range(n_pairs)]
 
 
@@ -187,10 +226,11 @@ def ransac_essential(src, dst, K, th: float = 0.01, max_iter: int = 2000, rng=No
     """Drop-in for homography.ransac_essential (:302-345) -> (refined E, inlier indices).
 
     With ``rng`` the 8-samples are the reference's own stream (``rng.choice(n, 8,
-    replace=False)`` per iteration); without it (every production caller) they are drawn
-    on the device.  All ``max_iter`` hypotheses are scored in one launch and the winner is
-    the one the sequential loop would have ended on (strict improvement, early exit above
-    0.8 n)."""
+    replace=False)`` per iteration) and the generator is left in the state the reference leaves
+    it in (only the iterations up to its early exit consumed); without it (every production
+    caller) they are drawn on the device.  All ``max_iter`` hypotheses are scored in one launch
+    and the winner is the one the sequential loop would have ended on (strict improvement, early
+    exit above 0.8 n)."""
     from b200slam.geometry import eight_point_refit
 
     src, dst = np.asarray(src), np.asarray(dst)

@@ -945,6 +945,119 @@ class SequencePipeline:
         return (self.s_up, self.s_compute, self.s_down)
 
 
+class PairPipeline:
+    """SequencePipeline's sibling for batches of INDEPENDENT pairs (loop-closure candidates, BASELINE config #3;
+    high-density pairs, config #4): `depth` steps in flight, each on its own stream — upload of the pairs'
+    descriptors and keypoints from pinned host memory, ONE CUDA graph with every kernel of the step, ONE download of
+    the result records.  Pair p's query / train rows live at p * rows_q / p * rows_t of the slot's device buffers
+    (fixed stride, so the copies are four contiguous transfers); the per-pair row counts may be ragged."""
+
+    def __init__(self, n_pairs: int, rows_q: int, rows_t: int, cfg: FrontendConfig, variant: int = _capi.VARIANT_I8MMA1,
+                 depth: int = 2, device=None, use_graph: bool = True, after_compute=None):
+        torch = _capi.require_cuda()
+        if not cfg.max_matches:
+            raise ValueError("PairPipeline needs max_matches (record stride)")
+        self.torch, self.cfg = torch, cfg
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.P, self.rq, self.rt, self.depth = int(n_pairs), int(rows_q), int(rows_t), max(1, depth)
+        self.after_compute, self.use_graph = after_compute, use_graph
+        self.rec_bytes = record_bytes(cfg.max_matches)
+        P = self.P
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "q": torch.empty((P * self.rq, DESC_BYTES), dtype=torch.uint8, device=self.dev),
+                "t": torch.empty((P * self.rt, DESC_BYTES), dtype=torch.uint8, device=self.dev),
+                "kq": torch.empty((P * self.rq, 2), dtype=torch.float32, device=self.dev),
+                "kt": torch.empty((P * self.rt, 2), dtype=torch.float32, device=self.dev),
+                "rec_dev": torch.empty((P, self.rec_bytes), dtype=torch.uint8, device=self.dev),
+                "rec_host": torch.empty((P, self.rec_bytes), dtype=torch.uint8).pin_memory(),
+                "fe": Frontend(cfg, variant=variant), "stream": torch.cuda.Stream(self.dev), "downloaded": torch.cuda.Event(),
+                "batch": None, "graph": None, "key": None, "res": None})
+        self.h2d_bytes = int(P * (self.rq + self.rt) * (DESC_BYTES + 8))
+        self.d2h_bytes = int(P * self.rec_bytes)
+        self._next = 0
+
+    def stage_host(self, qs, ts, kq, kt):
+        """Host lists of per-pair arrays -> pinned, fixed-stride staging buffers (done once per batch by the caller;
+        a real caller writes its frames straight into such buffers)."""
+        torch, P = self.torch, self.P
+        if not (len(qs) == len(ts) == len(kq) == len(kt) == P):
+            raise ValueError("stage_host: need exactly n_pairs entries")
+        q = np.zeros((P, self.rq, DESC_BYTES), np.uint8)
+        t = np.zeros((P, self.rt, DESC_BYTES), np.uint8)
+        a = np.zeros((P, self.rq, 2), np.float32)
+        b = np.zeros((P, self.rt, 2), np.float32)
+        nq, nt = np.zeros(P, np.int32), np.zeros(P, np.int32)
+        for p in range(P):
+            nq[p], nt[p] = len(qs[p]), len(ts[p])
+            if nq[p] > self.rq or nt[p] > self.rt:
+                raise ValueError("pair larger than the pipeline's row stride")
+            q[p, :nq[p]], t[p, :nt[p]] = _prep_desc(qs[p]), _prep_desc(ts[p])
+            a[p, :nq[p]], b[p, :nt[p]] = np.asarray(kq[p], np.float32).reshape(-1, 2), np.asarray(kt[p], np.float32).reshape(-1, 2)
+        pin = lambda x, w: torch.from_numpy(x.reshape(-1, w)).pin_memory()
+        return {"q": pin(q, DESC_BYTES), "t": pin(t, DESC_BYTES), "kq": pin(a, 2), "kt": pin(b, 2), "nq": nq, "nt": nt}
+
+    def _batch(self, sl, nq, nt):
+        torch, P = self.torch, self.P
+        q_off, t_off = np.zeros(P + 1, np.int32), np.zeros(P + 1, np.int32)
+        np.cumsum(nq, out=q_off[1:])
+        np.cumsum(nt, out=t_off[1:])
+        q_src = (np.arange(P, dtype=np.int64) * self.rq).astype(np.int32)
+        t_src = (np.arange(P, dtype=np.int64) * self.rt).astype(np.int32)
+        pack = torch.from_numpy(np.concatenate([q_off, t_off, q_src, t_src])).to(self.dev)
+        return PairBatch(q_desc=sl["q"], t_desc=sl["t"], q_off=pack[:P + 1], t_off=pack[P + 1:2 * P + 2], q_off_host=q_off, t_off_host=t_off,
+                         kp_q=sl["kq"], kp_t=sl["kt"], q_src=pack[2 * P + 2:3 * P + 2], t_src=pack[3 * P + 2:])
+
+    def _run_kernels(self, sl):
+        sl["res"] = sl["fe"].run(sl["batch"], records=sl["rec_dev"], pair_id0=0)
+        if self.after_compute is not None:
+            self.after_compute(sl)
+
+    def submit(self, staged) -> int:
+        torch = self.torch
+        i = self._next % self.depth
+        self._next += 1
+        sl = self.slots[i]
+        st = sl["stream"]
+        key = (staged["nq"].tobytes(), staged["nt"].tobytes())
+        if sl["key"] != key:                                   # new row counts: new CSR tables, new graph
+            st.synchronize()
+            sl["batch"], sl["key"], sl["graph"] = self._batch(sl, staged["nq"], staged["nt"]), key, None
+            with torch.cuda.stream(st):
+                for k in ("q", "t", "kq", "kt"):
+                    sl[k].copy_(staged[k], non_blocking=True)
+                self._run_kernels(sl)                          # eager once: lazy init, workspace
+            st.synchronize()
+            if self.use_graph:
+                g = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(g, stream=st):
+                        self._run_kernels(sl)
+                    sl["graph"] = g
+                except Exception:
+                    torch.cuda.synchronize()
+                    self.use_graph = False
+        with torch.cuda.stream(st):
+            for k in ("q", "t", "kq", "kt"):
+                sl[k].copy_(staged[k], non_blocking=True)
+            if sl["graph"] is not None:
+                sl["graph"].replay()
+            else:
+                self._run_kernels(sl)
+            sl["rec_host"].copy_(sl["rec_dev"], non_blocking=True)
+            sl["downloaded"].record(st)
+        return i
+
+    def result(self, slot: int):
+        sl = self.slots[slot]
+        sl["downloaded"].synchronize()
+        return RecordView(sl["rec_host"], self.cfg.max_matches)
+
+    def streams(self):
+        return tuple(sl["stream"] for sl in self.slots)
+
+
 class MapSweep:
     """BASELINE config #5 on one GPU: one query frame against EVERY keyframe of a persistent map (the loop of
     MapRelocalizer.relocalize, persistent_map.py:244-309, without the BoW cut to max_candidates), the map's

@@ -70,7 +70,7 @@ def decompose_essential(E: np.ndarray, src: np.ndarray, dst: np.ndarray, K: np.n
     return best
 
 
-# ---- homography branch (next-row #3: still host NumPy, batched) -------------------------
+# ---- homography branch: host pieces that follow the device RANSAC (K5 / K6) -------------------------
 
 def _normalise_batch(p: np.ndarray):
     """Hartley normalisation per sample set; p: (H, n, 2) (homography.py:118-125)."""
@@ -101,48 +101,6 @@ def dlt_homography_batch(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
     with np.errstate(all="ignore"):
         Hm = np.linalg.solve(Td, Hn @ Ts)
         return Hm / Hm[:, 2:3, 2:3]
-
-
-def ransac_homography(src, dst, th: float = 3.0, max_iter: int = 2000, rng=None):
-    """Batched restatement of ransac_homography (homography.py:148-216): same sampling
-    call, symmetric transfer error, strict-improvement + 0.8 n early-exit selection,
-    refit on the winner's inliers."""
-    src, dst = np.asarray(src, dtype=np.float64), np.asarray(dst, dtype=np.float64)
-    n = len(src)
-    if n < 4:
-        raise ValueError("At least four correspondences are required")
-    if rng is None:
-        rng = np.random.default_rng()
-        samples = np.argsort(rng.random((max_iter, n)), axis=1)[:, :4]
-    else:
-        samples = np.stack([rng.choice(n, 4, replace=False) for _ in range(max_iter)])
-    src_h, dst_h = _homog(src), _homog(dst)
-    best_h, best_count, best_mask = -1, 0, None
-    for lo in range(0, max_iter, 256):
-        idx = samples[lo:lo + 256]
-        Hs = dlt_homography_batch(src[idx], dst[idx])
-        with np.errstate(all="ignore"):
-            pf = src_h @ Hs.transpose(0, 2, 1)
-            pf = pf[..., :2] / pf[..., 2:3]
-            Hinv = np.linalg.pinv(Hs)
-            pb = dst_h @ Hinv.transpose(0, 2, 1)
-            pb = pb[..., :2] / pb[..., 2:3]
-            err = np.linalg.norm(pf - dst, axis=2) + np.linalg.norm(pb - src, axis=2)
-            masks = err < th
-        counts = masks.sum(axis=1)
-        done = False
-        for k, c in enumerate(counts):
-            if c > best_count:
-                best_h, best_count, best_mask = lo + k, int(c), masks[k]
-                if c > 0.8 * n:
-                    done = True
-                    break
-        if done:
-            break
-    if best_mask is None or best_count < 4:
-        raise RuntimeError("RANSAC failed — too few inliers")
-    inl = np.flatnonzero(best_mask)
-    return dlt_homography_batch(src[inl][None], dst[inl][None])[0], inl
 
 
 def decompose_homography(H, K=np.eye(3)):

@@ -98,23 +98,21 @@ class ShardedFrontend:
     """The hot path on this rank's block of a global pair batch + the gather of every rank's result records.
 
     ``n_pairs_global`` pairs are split with ``shard_bounds``; the caller builds the PairBatch of ITS pairs
-    (``self.lo .. self.hi``).  ``step(batch)`` runs match -> select -> hypotheses -> score -> winner -> refit ->
-    decomposition, the record kernel writes into this rank's slice of the gather buffer, and the all-gather
+    (``self.lo .. self.hi``).  ``step(batch)`` runs match -> select -> hypotheses -> score -> winner (-> refit ->
+    decomposition when cfg.with_pose), the record kernel writes into this rank's slice of the gather buffer, and the all-gather
     follows on the same stream.  ``capture(batch)`` records exactly that — collective included — into one CUDA
     graph (``replay()``); if the NCCL build cannot be captured the kernels are replayed and the collective is
     issued eagerly behind them (``gather_in_graph`` says which).  After a step every rank holds every pair's
     record (``records()`` -> device uint8 [n_pairs_global, record_bytes])."""
 
     def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None):
-        import dataclasses
-
         from . import _capi
         from .frontend import Frontend, record_bytes
 
         torch = _capi.require_cuda()
         if not cfg.max_matches:
             raise ValueError("ShardedFrontend needs max_matches (record stride)")
-        self.cfg = dataclasses.replace(cfg, with_pose=True)
+        self.cfg = cfg            # cfg.with_pose decides whether the records carry R | t (else zeros)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fe = Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant)
         self.rec_bytes = record_bytes(cfg.max_matches)

@@ -77,10 +77,21 @@ def cpu_model() -> str:
 
 
 def match_pair_cv2(q, t, ratio=0.8, max_matches=500):
-    """kNN-2 + ratio AND cross-check with OpenCV, sorted by distance, truncated."""
+    """kNN-2 + ratio AND cross-check with OpenCV, sorted by distance, truncated.  ratio=None: cross-check only
+    (the relocalizer's matcher, persistent_map.py:266-270)."""
     import cv2
 
     ref = reference_modules()
+    if ratio is None:
+        if ref:
+            if "cc" not in _ref_pipes:
+                _ref_pipes["cc"] = ref[1].ORBFeaturePipeline(ref[1].FeaturePipelineConfig(cross_check=True, max_matches=None))
+            ms = _ref_pipes["cc"].match(q, t)
+        else:
+            ms = sorted(cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(q, t), key=lambda m: m.distance)
+        ms = ms[:max_matches] if max_matches else ms
+        return (np.array([m.queryIdx for m in ms], np.int64), np.array([m.trainIdx for m in ms], np.int64),
+                np.array([m.distance for m in ms], np.int64))
     if ref:   # the reference's own ORBFeaturePipeline.match (.bak:78-95), in both of its modes
         key = float(ratio)
         if key not in _ref_pipes:
@@ -101,9 +112,11 @@ def match_pair_cv2(q, t, ratio=0.8, max_matches=500):
             np.array([m.distance for m in ms], np.int64))
 
 
-def cpu_pair(q, t, kq, kt, ratio=0.8, max_matches=500, th=0.01, max_iter=2000, seed=0, full_budget=False):
+def cpu_pair(q, t, kq, kt, ratio=0.8, max_matches=500, th=0.01, max_iter=2000, seed=0, full_budget=False, ransac=True):
     """One frame pair on the CPU -> (n_matches, best_h, n_inliers)."""
     qi, ti, _ = match_pair_cv2(q, t, ratio, max_matches)
+    if not ransac:
+        return len(qi), -1, 0
     if len(qi) < 8:
         return len(qi), -1, 0
     src, dst = kq[qi], kt[ti]

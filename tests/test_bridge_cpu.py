@@ -81,8 +81,11 @@ def test_host_refit_and_decompose_match_reference(golden_dir):
         np.testing.assert_allclose(t, rg[f"{name}/dec_t"], atol=1e-9)
 
 
-def test_host_homography_ransac_recovers_plane():
-    from b200slam.geometry import decompose_homography, ransac_homography
+def test_host_homography_refit_and_decomposition_recover_plane():
+    """The host pieces that follow the device homography RANSAC (n-point DLT refit, decompose_homography) behind the
+    oracle's CPU loop (the product has no CPU RANSAC: geometry.ransac_homography moved to oracle/)."""
+    from b200slam.geometry import decompose_homography, dlt_homography_batch
+    from oracle.homography_oracle import ransac_homography
     rng = np.random.default_rng(3)
     Ht = np.array([[1.02, 0.01, 5.0], [-0.02, 0.98, -3.0], [1e-5, 2e-5, 1.0]])
     src = rng.uniform(0, 640, (200, 2))
@@ -92,6 +95,7 @@ def test_host_homography_ransac_recovers_plane():
     H, inl = ransac_homography(src.astype(np.float32), dst.astype(np.float32), rng=np.random.default_rng(1))
     assert set(range(50, 200)) <= set(inl.tolist())
     np.testing.assert_allclose(H, Ht, atol=1e-3, rtol=1e-3)
+    np.testing.assert_allclose(dlt_homography_batch(src.astype(np.float32).astype(np.float64)[inl][None], dst.astype(np.float32).astype(np.float64)[inl][None])[0], H, atol=1e-8, rtol=1e-8)
     R, t = decompose_homography(H)
     np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
     with pytest.raises(ValueError):

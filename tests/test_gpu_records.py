@@ -142,14 +142,14 @@ def test_sharded_frontend_world1_graph_equals_eager_frontend():
     from b200slam.sharding import ShardedFrontend
     S = 300
     b, _, _ = _seq_batch(9, 700, 33)
-    cfg = FrontendConfig(hypotheses=256, max_matches=S)
+    cfg = FrontendConfig(hypotheses=256, max_matches=S, with_pose=True)
     sf = ShardedFrontend(cfg, b.n_pairs)
     sf.capture(b)
     sf.replay()
     torch.cuda.synchronize()
     got = unpack_records(sf.records().cpu().numpy(), S)
     ref = torch.zeros((b.n_pairs, record_bytes(S)), dtype=torch.uint8, device="cuda")
-    Frontend(dataclasses.replace(cfg, with_pose=True)).run(b, records=ref)
+    Frontend(cfg).run(b, records=ref)
     want = unpack_records(ref.cpu().numpy(), S)
     for k in want:
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)

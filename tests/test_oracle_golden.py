@@ -190,3 +190,21 @@ def test_fivepoint_oracle_matches_cv2(golden_dir):
         mine += len(E)
         hit += fp.match_solution_sets(g[f"c{k}/E"], E, 1e-6)
     assert total > 200 and hit >= total - 2 and mine <= total + 2, (total, hit, mine)
+
+
+def test_oracle_reproduces_the_reference_estimator_essential_branch(golden_dir):
+    """pose_golden.npz (unmodified RobustPoseEstimator.estimate_pose, seeded): where the essential model won, the
+    oracle's ransac_essential with the recorded seed and the adaptive threshold returns the very inlier set."""
+    from oracle import hamming_oracle as ho
+    from oracle import ransac_oracle as ro
+    pg = np.load(golden_dir / "pose_golden.npz")
+    checked = 0
+    for name in (str(n) for n in pg["names"]):
+        if str(pg[f"{name}/outcome"]) != "estimate" or str(pg[f"{name}/method"]) != "essential":
+            continue
+        p1, p2 = pg[f"{name}/pts1"], pg[f"{name}/pts2"]
+        th = ho.adaptive_ransac_threshold(p1, p2, 0.01, 0.005, 0.02)
+        _, inl = ro.ransac_essential(p1, p2, np.eye(3), th, 2000, np.random.default_rng(int(pg[f"{name}/seed0"])))
+        np.testing.assert_array_equal(inl, pg[f"{name}/inlier_indices"], err_msg=name)
+        checked += 1
+    assert checked >= 2

@@ -28,7 +28,7 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 S = 200
-cfg = FrontendConfig(hypotheses=256, max_matches=S, threshold=0.01, seed=99)
+cfg = FrontendConfig(hypotheses=256, max_matches=S, threshold=0.01, seed=99, with_pose=True)
 out = {}
 in_graph = None
 if a.config == 3:
