@@ -405,9 +405,9 @@ class Env:
         return float(tt.item())
 
     def finish(self):
-        if self.world > 1:
-            self.dist.barrier()
-            self.dist.destroy_process_group()
+        if self.world > 1:      # every run_config* has returned: its graphs (which captured the collective) are gone
+            from b200slam.sharding import shutdown_process_group
+            shutdown_process_group()
 
 
 def _capture(env, fn, use_graph=True):
@@ -625,6 +625,31 @@ def run_config2(env, a):
     pairs_per_step = world * P * a.sub_batches
     value = pairs_per_step * a.steps / (total_ms * 1e-3)
 
+    # ---- sustained behaviour: the step replayed back to back for >= 2 s (clocks / power sampled over it) ----
+    soak = None
+    if world == 1 or rank == 0:
+        n_soak = max(10, int(2.2e3 / max(total_ms / a.steps, 1e-3)))
+    if world > 1:
+        t_n = torch.tensor([n_soak if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(t_n, src=0)
+        n_soak = int(t_n.item())
+    soak_clk = Clocks(env.local)
+    env.barrier()
+    if rank == 0:
+        soak_clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_soak):
+        step()
+    e1.record()
+    env.barrier()
+    soak_ms = env.max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        sc = soak_clk.stop()
+        soak = {"seconds": soak_ms * 1e-3, "steps": n_soak, "value": pairs_per_step * n_soak / (soak_ms * 1e-3), "unit": UNIT,
+                "sm_mhz": sc["sm_mhz"], "power_w_max": sc["power_w_max"], "reasons": sc["reasons"], "clock_samples": sc["samples"],
+                "note": "the timed step replayed back to back without L2 flushes; sustained clocks and power next to the 20-step figure"}
+
     # ---- the same step, additionally refitting E on the inliers and recovering (R, t) (K7) into the records ----
     import dataclasses
     sfp = ShardedFrontend(dataclasses.replace(cfg, with_pose=True), world * P, variant=env.variant)
@@ -636,6 +661,18 @@ def run_config2(env, a):
     ms_p = env.timed(step_p, max(3, a.steps // 2), 2)
     value_pose = pairs_per_step * len(ms_p) / (env.max_over_ranks(float(np.sum(ms_p))) * 1e-3)
     del sfp
+    # ---- the same step with winner-only scoring: identical winner / inlier mask, hypotheses that cannot win abandoned early ----
+    sfw = ShardedFrontend(dataclasses.replace(cfg, winner_only=True), world * P, variant=env.variant)
+
+    def step_winner():
+        for i in range(a.sub_batches):
+            sfw.step(batches[i % W])
+    step_w, launches_w, _ = _capture(env, step_winner, use_graph=not a.no_graph)
+    ms_w = env.timed(step_w, max(3, a.steps // 2), 2)
+    value_winner = pairs_per_step * len(ms_w) / (env.max_over_ranks(float(np.sum(ms_w))) * 1e-3)
+    same_winner = bool(torch.equal(sfw.res.best_h, sf.res.best_h) and torch.equal(sfw.res.best_count, sf.res.best_count)
+                       and torch.equal(sfw.res.inlier_mask, sf.res.inlier_mask))
+    del sfw
 
     fe = sf.fe
     # ---- dominant kernel alone + the decision record of the three Hamming kernels ----
@@ -731,7 +768,13 @@ def run_config2(env, a):
            "cuda_graph": pipe.use_graph, "steps_in_flight": depth, "d2h_copies_per_launch_set": 1,
            "timing": "one CUDA-event pair around all K steps (steps overlap); inputs arrive over PCIe from pinned host memory every launch set",
            "cpu_affinity_first_count": env.numa, "ms_per_step": e2e_total / a.steps, "result_check": e2e_check}
-    extra = {"value_cuda_graph": graphed, "collective_in_graph": bool(sf.world > 1 and graphed),
+    extra = {"value_cuda_graph": graphed, "collective_in_graph": bool(sf.world > 1 and graphed), "soak": soak,
+             "value_winner_only": value_winner,
+             "value_winner_only_note": "same step through b2s_ransac_winner_batched: the winner, its inlier count and mask are those of the full "
+                                       "evaluation (checked on the last launch set: %s), but only the hypotheses that can still exceed 0.8 M or reach the "
+                                       "largest complete count are scored to the end; reported beside, not instead of, `value` (all %d hypotheses scored)"
+                                       % (same_winner, a.hyps),
+             "winner_only_identical": same_winner, "gpu_launches_per_step_winner_only": launches_w,
              "value_with_pose": value_pose,
              "value_with_pose_note": "same step + n-point refit of E on the winner's inliers + decomposition / cheirality vote (K7), R | t in the records; "
                                      "outside the metric's unit (SURVEY 8d), reported beside it",
@@ -1052,6 +1095,9 @@ def _bind_to_gpu_numa_node(local: int):
 
 
 def main():
+    import faulthandler
+    # a stuck collective or kernel must end with a traceback, never by hanging the box until the harness kills it
+    faulthandler.dump_traceback_later(int(os.environ.get("B2S_WATCHDOG_S", "840")), exit=True)
     a = parse()
     if a.impl == "reference":
         reference_main(a)

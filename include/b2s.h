@@ -293,6 +293,20 @@ int b2s_pack_records(const int32_t* count, const int32_t* count_total, const int
 int b2s_rank_pairs(const int32_t* score, const int32_t* ids, const int32_t* sel_count, int n, int k, int stride,
                    int32_t* top_idx, int32_t* top_id, int32_t* c_off, int32_t* c_count, void* stream);
 
+/* ---- winner only: the reference's answer without scoring every hypothesis to the end ----------------
+ * best_h / best_count / inlier_mask exactly as b2s_ransac_score_batched(precision 64) + b2s_ransac_select
+ * return them, but a hypothesis is abandoned as soon as it can neither exceed 0.8 * M nor reach the largest
+ * complete count (homography.py:335-339): all H hypotheses are scored on the first ~3/8 of the correspondences,
+ * the 8 most promising are finished to get a lower bound of the maximum, and only the hypotheses whose upper
+ * bound reaches it are finished.  counts_out (optional, [pair][H]) receives complete counts for the finished
+ * hypotheses and lower bounds for the abandoned ones; n_finished_out (optional, [pair]) the number finished in
+ * the last pass.  workspace: b2s_ransac_winner_workspace_bytes, 16-byte aligned. */
+size_t b2s_ransac_winner_workspace_bytes(int n_pairs, int H);
+int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
+                              int H, double th2, const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
+                              uint8_t* inlier_mask, void* workspace, size_t workspace_bytes, int32_t* counts_out,
+                              int32_t* n_finished_out, void* stream);
+
 /* ---- measurement helper ----------------------------------------------------------
  * Saturates one SM pipe with independent instructions to measure its rate:
  * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD, 7 REDUX.MIN, 8 SHFL.

@@ -103,6 +103,10 @@ def _declare(lib):
     lib.b2s_bow_histogram_batched.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     lib.b2s_bow_cosine.restype = i32
     lib.b2s_bow_cosine.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.b2s_ransac_winner_workspace_bytes.restype = sz
+    lib.b2s_ransac_winner_workspace_bytes.argtypes = [i32, i32]
+    lib.b2s_ransac_winner_batched.restype = i32
+    lib.b2s_ransac_winner_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp, sz, vp, vp, vp]
     lib.b2s_ransac_select.restype = i32
     lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
     lib.b2s_hamming_i8_debug.restype = None
@@ -126,7 +130,7 @@ EXPORTS = (
     "b2s_hamming_i8_debug", "b2s_hamming_kernel_timing", "b2s_ransac_score_tc_workspace_bytes", "b2s_ransac_score_tc",
     "b2s_homography_dlt_batched", "b2s_homography_score_batched", "b2s_homography_select", "b2s_decompose_essential_batched", "b2s_refit_essential_batched", "b2s_pose_pick", "b2s_five_point_batched",
     "b2s_bow_histogram_batched", "b2s_bow_cosine", "b2s_hamming_shared_workspace_bytes", "b2s_hamming_knn2_shared", "b2s_hamming_last_plan",
-    "b2s_record_bytes", "b2s_pack_records", "b2s_rank_pairs",
+    "b2s_record_bytes", "b2s_pack_records", "b2s_rank_pairs", "b2s_ransac_winner_workspace_bytes", "b2s_ransac_winner_batched",
 )
 
 

@@ -379,6 +379,27 @@ class EssentialRansac:
             precision, int(max_m), ptr(counts), current_stream()))
         return counts[:n_pairs, :H]
 
+    def winner(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, return_counts: bool = False):
+        """Winner-only scoring (b2s_ransac_winner_batched): best_h / best_count / inlier mask identical to
+        score(precision=64) + select, but hypotheses that can neither exceed 0.8 M nor reach the largest complete count
+        are abandoned after the first ~3/8 of the correspondences.  return_counts: also (counts [pair, H] — complete
+        for finished hypotheses, lower bounds for abandoned ones — and the number finished per pair)."""
+        torch = _capi.require_cuda()
+        H, dev = E.shape[1], corr.device
+        best_h = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=dev)
+        best_c = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=dev)
+        mask = torch.zeros(max(corr.shape[0], 1), dtype=torch.uint8, device=dev)
+        need = int(self._lib.b2s_ransac_winner_workspace_bytes(n_pairs, H))
+        if getattr(self, "_win_ws", None) is None or self._win_ws.numel() < need or self._win_ws.device != dev:
+            self._win_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        counts = torch.empty((max(n_pairs, 1), max(H, 1)), dtype=torch.int32, device=dev) if return_counts else None
+        nfin = torch.zeros(max(n_pairs, 1), dtype=torch.int32, device=dev) if return_counts else None
+        check(self._lib.b2s_ransac_winner_batched(
+            ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2), ptr(th2_per_pair), ptr(best_h), ptr(best_c),
+            ptr(mask), self._win_ws.data_ptr(), need, ptr(counts), ptr(nfin), current_stream()))
+        out = (best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]])
+        return out + (counts[:n_pairs, :H], nfin[:n_pairs]) if return_counts else out
+
     def select(self, counts, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None):
         torch = _capi.require_cuda()
         H = E.shape[1]
@@ -623,6 +644,8 @@ class FrontendConfig:
     with_pose: bool = False    # also refit E on the winner's inliers and recover (R, t) on the device (K7)
     scoring: str = "cuda"      # "cuda": K3h on the CUDA cores (default, 0.30 ms per 296-pair step); "tc": K3t tensor-core
                                # scoring (0.35 ms).  Same counts.
+    winner_only: bool = False  # True: same winner / inlier mask, but hypotheses that cannot win are abandoned early
+                               # (EssentialRansac.winner); FrontendResult.counts is then None
 
 
 @dataclass
@@ -671,8 +694,12 @@ class Frontend:
         E = self.ransac.hypotheses(sel.corr, sel.c_off, sel.count, b.n_pairs, c.hypotheses,
                                    samples=samples, seed=c.seed, K=K, pair_id0=pair_id0)
         th2 = c.threshold ** 2
-        counts = self.score(sel, b, E)
-        best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
+        if c.winner_only:
+            counts = None
+            best_h, best_c, mask = self.ransac.winner(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
+        else:
+            counts = self.score(sel, b, E)
+            best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
         res = FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
         if c.with_pose:      # next-row #2: refit on the winner's inliers + decomposition / cheirality vote (K7)
             if self.pose is None:
@@ -851,6 +878,11 @@ class SequencePipeline:
     # ---- shared -----------------------------------------------------------------------------------------
     def _run_kernels(self, sl):
         sl["res"] = sl["fe"].run(sl["batch"], records=sl["rec_dev"], pair_id0=0)
+
+    def _after(self, sl):
+        # A collective hook runs EAGERLY behind the slot's graph, never inside it: graphs of different slots replay on
+        # different streams with no mutual order, and two ranks must issue a communicator's collectives in the same
+        # order — torch's process group serialises eager calls on its own stream in program order, a graph node does not.
         if self.after_compute is not None:
             self.after_compute(sl)
 
@@ -865,6 +897,7 @@ class SequencePipeline:
             st = sl["stream"] or self.s_compute
             with torch.cuda.stream(st):
                 self._run_kernels(sl)                                     # eager once: lazy init, workspace
+                self._after(sl)
             st.synchronize()
             if self.use_graph and self.schedule == "serial":
                 g = torch.cuda.CUDAGraph()
@@ -908,6 +941,7 @@ class SequencePipeline:
                 sl["graph"].replay()
             else:
                 self._run_kernels(sl)
+            self._after(sl)
             sl["rec_host"].copy_(sl["rec_dev"], non_blocking=True)      # the step's ONE download
             sl["downloaded"].record(st)
 
@@ -928,6 +962,7 @@ class SequencePipeline:
                 sl["graph"].replay()
             else:
                 self._run_kernels(sl)
+            self._after(sl)
             sl["computed"].record(self.s_compute)
         self.s_down.wait_event(sl["computed"])
         with torch.cuda.stream(self.s_down):
@@ -1011,8 +1046,6 @@ class PairPipeline:
 
     def _run_kernels(self, sl):
         sl["res"] = sl["fe"].run(sl["batch"], records=sl["rec_dev"], pair_id0=0)
-        if self.after_compute is not None:
-            self.after_compute(sl)
 
     def submit(self, staged) -> int:
         torch = self.torch
@@ -1045,6 +1078,8 @@ class PairPipeline:
                 sl["graph"].replay()
             else:
                 self._run_kernels(sl)
+            if self.after_compute is not None:                 # eager, behind the graph (see SequencePipeline._after)
+                self.after_compute(sl)
             sl["rec_host"].copy_(sl["rec_dev"], non_blocking=True)
             sl["downloaded"].record(st)
         return i

@@ -30,7 +30,7 @@ def eight_point_refit(src: np.ndarray, dst: np.ndarray, K: np.ndarray) -> np.nda
     b = b / b[:, 2:3]
     x, y, u, v = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
     A = np.stack([u * x, u * y, u, v * x, v * y, v, x, y, np.ones(n)], axis=1)
-    F = np.linalg.svd(A)[2][-1].reshape(3, 3)
+    F = np.linalg.svd(A, full_matrices=False)[2][-1].reshape(3, 3)    # economy form: the reference's full U is n x n and unused
     U, S, Vt = np.linalg.svd(F)
     S[2] = 0.0
     return K.T @ (U @ np.diag(S) @ Vt) @ K

@@ -50,6 +50,36 @@ def gather_records(local, n_items: int, group=None):
     return g.ordered()
 
 
+def shutdown_process_group(timeout_s: float = 20.0):
+    """Destroy the default process group at the end of a run.  CUDA graphs that captured NCCL collectives must be
+    released BEFORE their communicator is destroyed (ncclCommDestroy waits for them forever otherwise — measured: a
+    15-minute hang): the caller drops its ShardedFrontend / ShardedSweep objects first, this collects what is left,
+    and a timer ends the process normally if the teardown still does not return."""
+    import gc
+    import os
+    import sys
+    import threading
+
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Timer(timeout_s, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
+
+
 class RecordGather:
     """Persistent gather buffer [world, cap, width]: ``local`` (this rank's [cap, width] slice) is where the last
     kernel of a step writes; ``all_gather()`` completes the other slices in place (NCCL recognises
@@ -162,6 +192,10 @@ class ShardedFrontend:
     def records(self):
         return self.gather.ordered()
 
+    def close(self):
+        """Release the captured graph (it holds the NCCL all-gather node: see shutdown_process_group)."""
+        self._graph = None
+
 
 class ShardedSweep:
     """BASELINE config #5 on N GPUs: keyframes sharded by id (contiguous blocks), each shard resident on its GPU
@@ -231,6 +265,9 @@ class ShardedSweep:
             self._graph.replay()
         else:
             self.query()
+
+    def close(self):
+        self._graph = None
 
     def result_host(self):
         """-> (per-keyframe match counts in global keyframe order, the global top-k candidates as a dict of arrays

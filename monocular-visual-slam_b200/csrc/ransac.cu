@@ -84,21 +84,43 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 constexpr int kScoreHThreads = 128;
 constexpr int kScoreHChunk = 512;   // 8 KB of shared memory: the usual pair (<= 500 correspondences) is staged once, in the pass that also finds W1 / W2
 
+// Winner-only scoring (b2s_ransac_winner_batched) evaluates a hypothesis in two pieces: every hypothesis on the
+// first screen_len(M) correspondences, and only those that can still win on the rest.
+__host__ __device__ inline int screen_len(int M) { return M <= 64 ? M : min(M, ((3 * M) / 8 + 31) & ~31); }
+
+// MODE 0: all correspondences (or the gridDim.z slice), counts written / atomically added.
+// MODE 1: the screening prefix [0, screen_len(M)), counts written.
+// MODE 2: the rest [screen_len(M), M) for the hypotheses listed in `list` (n_list[pair] of them per pair), added
+//         to the count the screening pass left (single writer per hypothesis).
+template <int MODE>
 __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
     const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp,
-    int32_t* __restrict__ counts) {
+    int32_t* __restrict__ counts, const int32_t* __restrict__ list, const int32_t* __restrict__ n_list) {
   __shared__ float4 s_p[kScoreHChunk];
   __shared__ float s_w[2];
   const int pair = blockIdx.y;
-  const int h = blockIdx.x * kScoreHThreads + threadIdx.x;
+  int h = blockIdx.x * kScoreHThreads + threadIdx.x;
+  int n_h = H;
+  if (MODE == 2) {
+    n_h = n_list[pair];
+    if ((int)blockIdx.x * kScoreHThreads >= n_h) return;   // uniform for the CTA
+    h = h < n_h ? list[(size_t)pair * H + h] : 0;
+  }
   // gridDim.z > 1: the pair's correspondences are cut into gridDim.z slices (multiples of 32) and the counts
   // are summed with atomicAdd into a zeroed array — a lone pair with thousands of correspondences (BASELINE
   // config #4: 4096 hypotheses x ~7000 matches = 32 CTAs otherwise) then fills the machine.  The rounding bound
   // only needs W1 / W2 >= the norms of the correspondences this CTA evaluates, so the slice's own maxima serve.
   int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   const float4* cp = corr + c_off[pair];
-  if (gridDim.z > 1) {
+  if (MODE == 1) M = screen_len(M);
+  if (MODE == 2) {
+    const int lo = screen_len(M);
+    M -= lo;
+    cp += lo;
+    if (M <= 0) return;   // uniform for the CTA: the screening pass already saw everything
+  }
+  if (MODE == 0 && gridDim.z > 1) {
     const int per = (((M + (int)gridDim.z - 1) / (int)gridDim.z) + 31) & ~31;
     const int lo = min(M, (int)blockIdx.z * per);
     M = min(M, lo + per) - lo;
@@ -107,7 +129,7 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   }
   const double th2d = th2_pp ? th2_pp[pair] : th2_all;
   const float th2 = (float)th2d;
-  const bool live = h < H;
+  const bool live = MODE == 2 ? (int)(blockIdx.x * kScoreHThreads + threadIdx.x) < n_h : h < H;
   double ed[9];
   float e[9];
   float n2 = 0.0f;
@@ -220,9 +242,126 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     }
   }
   if (live) {
-    if (gridDim.z > 1) atomicAdd(&counts[(size_t)pair * H + h], count);
+    if (MODE == 2) counts[(size_t)pair * H + h] += count;
+    else if (MODE == 0 && gridDim.z > 1) atomicAdd(&counts[(size_t)pair * H + h], count);
     else counts[(size_t)pair * H + h] = count;
   }
+}
+
+// ---- winner-only: which hypotheses can still win after the screening pass ------------------------------
+// One CTA per pair.  c1[h] = inliers among the first m1 = screen_len(M) correspondences, so
+// c1[h] <= count[h] <= ub[h] = c1[h] + (M - m1).  The kBoundTop hypotheses with the largest c1 are finished here
+// (float64, the rest of the correspondences) and give L = the largest COMPLETE count.  A hypothesis matters to
+// the reference's rule (first h above 0.8 M, else the lowest h among the maximum, homography.py:335-339) only if
+// it can exceed 0.8 M or reach the maximum; ub[h] < min(L, floor(0.8 M) + 1) rules out both (the maximum is >= L).
+// Everything else is listed (ascending h) for the finishing pass.  The abandoned hypotheses keep c1[h] in
+// `counts`: a lower bound that is <= 0.8 M and < L, so the ordinary winner kernel run over ALL of `counts`
+// returns exactly the winner of the full evaluation.
+constexpr int kBoundThreads = 256;
+constexpr int kBoundTop = 8;
+
+__global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
+    const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
+    const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp, int32_t* __restrict__ counts,
+    int32_t* __restrict__ list, int32_t* __restrict__ n_list) {
+  __shared__ unsigned long long s_red[kBoundThreads / 32];
+  __shared__ unsigned long long s_top[kBoundTop];
+  __shared__ int s_cnt[kBoundTop];
+  __shared__ int s_scan[kBoundThreads / 32];
+  __shared__ int s_need;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = max(c_count[pair], 0), m1 = screen_len(M);
+  int32_t* cnt = counts + (size_t)pair * H;
+  const float4* cp = corr + c_off[pair];
+  const double th2 = th2_pp ? th2_pp[pair] : th2_all;
+  if (M == m1) {   // nothing left to evaluate: every count is complete, nobody needs finishing
+    if (tid == 0) n_list[pair] = 0;
+    return;
+  }
+  if (tid < kBoundTop) s_cnt[tid] = 0;
+  // ---- the kBoundTop largest c1 (ties: lower h), kBoundTop rounds of a block arg-max below the previous key ----
+  unsigned long long last = ~0ull;
+  for (int r = 0; r < kBoundTop; ++r) {
+    unsigned long long best = 0ull;
+    for (int h = tid; h < H; h += kBoundThreads) {
+      const unsigned long long key = ((unsigned long long)(uint32_t)cnt[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
+      if (key < last && key > best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+      best = v > best ? v : best;
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    best = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kBoundThreads / 32; ++w) best = s_red[w] > best ? s_red[w] : best;
+    if (tid == 0) s_top[r] = best;
+    last = best;          // 0 when fewer than r + 1 hypotheses exist: later rounds find nothing
+    __syncthreads();
+  }
+  // ---- finish them: the correspondences [m1, M), float64 ----
+  for (int r = 0; r < kBoundTop; ++r) {
+    const unsigned long long key = s_top[r];
+    if (key == 0ull) break;                                   // uniform
+    const int h = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    double e[9];
+    const double* ep = E + ((size_t)pair * H + h) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) e[k] = ep[k];
+    int mine = 0;
+    for (int m = m1 + tid; m < M; m += kBoundThreads) {
+      const float4 c = cp[m];
+      mine += sampson_inlier<double>(e, (double)c.x, (double)c.y, (double)c.z, (double)c.w, th2) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_cnt[r], mine);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int L = 0;
+    for (int r = 0; r < kBoundTop; ++r) {
+      if (s_top[r] == 0ull) break;
+      const int h = (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull));
+      const int full = (int)(s_top[r] >> 32) + s_cnt[r];
+      cnt[h] = full;                                           // complete
+      L = max(L, full);
+    }
+    const int early = (int)floor(0.8 * (double)M) + 1;         // smallest count with count > 0.8 * M (float64, as the reference compares)
+    s_need = min(L, early) - (M - m1);                         // survive iff c1[h] >= need
+  }
+  __syncthreads();
+  // ---- ordered compaction of the survivors (the finished ones excluded) ----
+  const int need = s_need;
+  const int per = (H + kBoundThreads - 1) / kBoundThreads;
+  const int h0 = tid * per, h1 = min(H, h0 + per);
+  int mine = 0;
+  for (int h = h0; h < h1; ++h) {
+    bool done = false;
+#pragma unroll
+    for (int r = 0; r < kBoundTop; ++r) done |= (s_top[r] != 0ull && (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull)) == h);
+    mine += (!done && cnt[h] >= need) ? 1 : 0;
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_scan[w];
+  int pos = base + incl - mine;
+  for (int h = h0; h < h1; ++h) {
+    bool done = false;
+#pragma unroll
+    for (int r = 0; r < kBoundTop; ++r) done |= (s_top[r] != 0ull && (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull)) == h);
+    if (!done && cnt[h] >= need) list[(size_t)pair * H + pos++] = h;
+  }
+  if (tid == kBoundThreads - 1) n_list[pair] = base + incl;
 }
 
 // ---- winner selection + inlier mask ---------------------------------------------------
@@ -439,11 +578,48 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
       B2S_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * H, st));
       grid.z = zs;
     }
-    ransac_score_hybrid_kernel<<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts);
+    ransac_score_hybrid_kernel<0><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr);
   } else if (precision == 6464)
     ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
   else
     ransac_score_kernel<float><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
+  B2S_CUDA(cudaGetLastError());
+  note_launch();
+  return B2S_OK;
+}
+
+size_t b2s_ransac_winner_workspace_bytes(int n_pairs, int H) {
+  if (n_pairs <= 0 || H <= 0) return 0;
+  return sizeof(int32_t) * ((size_t)n_pairs * H * 2 + (size_t)n_pairs) + 256;   // counts | survivor list | survivors per pair
+}
+
+int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
+                              int H, double th2, const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
+                              uint8_t* inlier_mask, void* workspace, size_t workspace_bytes, int32_t* counts_out,
+                              int32_t* n_finished_out, void* stream) {
+  using namespace b2s;
+  B2S_REQUIRE(corr && c_off && c_count && E && best_h && best_count && inlier_mask, "null pointer");
+  B2S_REQUIRE(n_pairs >= 0 && H >= 0, "negative size");
+  B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
+  if (n_pairs == 0) return B2S_OK;
+  B2S_REQUIRE(workspace && workspace_bytes >= b2s_ransac_winner_workspace_bytes(n_pairs, H) && ((uintptr_t)workspace & 15u) == 0,
+              "winner-only scoring needs b2s_ransac_winner_workspace_bytes(n_pairs, H) bytes, 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* c4 = reinterpret_cast<const float4*>(corr);
+  int32_t* counts = counts_out ? counts_out : static_cast<int32_t*>(workspace);
+  int32_t* list = static_cast<int32_t*>(workspace) + (size_t)n_pairs * H;
+  int32_t* n_list = n_finished_out ? n_finished_out : list + (size_t)n_pairs * H;
+  if (H > 0) {
+    dim3 grid((H + kScoreHThreads - 1) / kScoreHThreads, n_pairs);
+    ransac_score_hybrid_kernel<1><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr);
+    B2S_CUDA(cudaGetLastError());
+    ransac_bound_kernel<<<n_pairs, kBoundThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, list, n_list);
+    B2S_CUDA(cudaGetLastError());
+    ransac_score_hybrid_kernel<2><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, list, n_list);
+    B2S_CUDA(cudaGetLastError());
+    note_launch(3);
+  }
+  ransac_select_kernel<<<n_pairs, 256, 0, st>>>(counts, c4, c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count, inlier_mask);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;

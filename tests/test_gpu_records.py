@@ -165,10 +165,10 @@ def test_two_gpus_equal_one_gpu(config, tmp_path):
     out1, out2 = tmp_path / "w1.npz", tmp_path / "w2.npz"
     env = dict(os.environ, PYTHONPATH=f"{ROOT}{os.pathsep}{ROOT / 'monocular-visual-slam_b200'}")
     tool = str(ROOT / "tools" / "sharded_check.py")
-    r1 = subprocess.run([sys.executable, tool, "--config", str(config), "--out", str(out1)], env=env, capture_output=True, text=True, timeout=600)
+    r1 = subprocess.run([sys.executable, tool, "--config", str(config), "--out", str(out1)], env=env, capture_output=True, text=True, timeout=300)
     assert r1.returncode == 0, r1.stderr[-3000:]
     r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                         "--master-port", "29517", tool, "--config", str(config), "--out", str(out2)], env=env, capture_output=True, text=True, timeout=900)
+                         "--master-port", "29517", tool, "--config", str(config), "--out", str(out2)], env=env, capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0, r2.stderr[-3000:]
     a, b = np.load(out1), np.load(out2)
     assert set(a.files) == set(b.files) and len(a.files) > 3

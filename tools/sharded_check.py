@@ -3,6 +3,7 @@ writes the gathered result records of a small config #3 batch (pair-sharded Shar
 config #5 sweep (keyframe-sharded ShardedSweep) to --out on rank 0.  tests/test_gpu_records.py compares the
 world-1 and world-2 files bit for bit."""
 import argparse
+import faulthandler
 import json
 import os
 import sys
@@ -18,9 +19,11 @@ from b200slam.frontend import FrontendConfig, PairBatch, unpack_records
 from b200slam.sharding import ShardedFrontend, ShardedSweep, shard_bounds
 from b200slam.synthetic import tracking_pairs
 
+faulthandler.dump_traceback_later(int(os.environ.get("B2S_WATCHDOG_S", "120")), exit=True)   # a stuck collective must not hang the box
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=3)
 ap.add_argument("--out", required=True)
+ap.add_argument("--no-graph-collective", action="store_true", help="keep the collective out of the CUDA graph (diagnostics)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -31,13 +34,16 @@ S = 200
 cfg = FrontendConfig(hypotheses=256, max_matches=S, threshold=0.01, seed=99, with_pose=True)
 out = {}
 in_graph = None
+sf = sw = None
 if a.config == 3:
     n = 21                                                     # not divisible by 2: exercises the padded shard
     qs, ts, kq, kt = tracking_pairs(n, 500, seed=5, keep=0.4, ragged=True)
     sf = ShardedFrontend(cfg, n)
     lo, hi = sf.lo, sf.hi
     batch = PairBatch.from_host(qs[lo:hi], ts[lo:hi], kq[lo:hi], kt[lo:hi])
-    in_graph = sf.capture(batch)
+    print(f"[rank {rank}] eager step ok, capturing", file=sys.stderr, flush=True)
+    in_graph = sf.capture(batch, collective_in_graph=not a.no_graph_collective)
+    print(f"[rank {rank}] captured, collective_in_graph={in_graph}", file=sys.stderr, flush=True)
     for _ in range(2):
         sf.replay()
     torch.cuda.synchronize()
@@ -70,7 +76,9 @@ else:
         sw.query(torch.from_numpy(q_desc).cuda(), torch.from_numpy(q_kp).cuda(), n_rows=nq)
     else:
         sw.query(n_rows=nq)
-    in_graph = sw.capture()
+    print(f"[rank {rank}] eager query ok, capturing", file=sys.stderr, flush=True)
+    in_graph = sw.capture() if not a.no_graph_collective else False
+    print(f"[rank {rank}] captured={in_graph}", file=sys.stderr, flush=True)
     sw.replay()
     torch.cuda.synchronize()
     counts, cand = sw.result_host()
@@ -79,6 +87,7 @@ if rank == 0:
     np.savez(a.out, **out)
     print(json.dumps({"world": world, "config": a.config, "collective_in_graph": in_graph,
                       "summary": {k: np.asarray(v).reshape(-1)[:5].tolist() for k, v in out.items() if k in ("n_matches", "inliers", "pair_id", "counts")}}))
+sf = sw = None          # graphs that captured the collective go before their communicator
 if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+    from b200slam.sharding import shutdown_process_group
+    shutdown_process_group()
