@@ -96,13 +96,16 @@ template <int MODE>
 __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
     const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp,
-    int32_t* __restrict__ counts, const int32_t* __restrict__ list, const int32_t* __restrict__ n_list) {
+    int32_t* __restrict__ counts, const int32_t* __restrict__ list, const int32_t* __restrict__ n_list,
+    int h_first, int h_end, const int32_t* __restrict__ early) {
   __shared__ float4 s_p[kScoreHChunk];
   __shared__ float s_w[2];
   const int pair = blockIdx.y;
-  int h = blockIdx.x * kScoreHThreads + threadIdx.x;
-  int n_h = H;
+  if (early && early[pair] >= 0) return;   // winner-only: this pair's answer is already known (uniform for the CTA)
+  int h = h_first + blockIdx.x * kScoreHThreads + threadIdx.x;   // MODE 0 / 1 score the hypotheses [h_first, h_end)
+  int n_h = h_end;
   if (MODE == 2) {
+    h -= h_first;
     n_h = n_list[pair];
     if ((int)blockIdx.x * kScoreHThreads >= n_h) return;   // uniform for the CTA
     h = h < n_h ? list[(size_t)pair * H + h] : 0;
@@ -129,12 +132,12 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   }
   const double th2d = th2_pp ? th2_pp[pair] : th2_all;
   const float th2 = (float)th2d;
-  const bool live = MODE == 2 ? (int)(blockIdx.x * kScoreHThreads + threadIdx.x) < n_h : h < H;
+  const bool live = MODE == 2 ? (int)(blockIdx.x * kScoreHThreads + threadIdx.x) < n_h : h < h_end;
   double ed[9];
   float e[9];
   float n2 = 0.0f;
   {
-    const double* ep = E + ((size_t)pair * H + (live ? h : 0)) * 9;
+    const double* ep = E + ((size_t)pair * H + (live ? h : h_first)) * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       ed[k] = ep[k];
@@ -248,8 +251,12 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   }
 }
 
-// ---- winner-only: which hypotheses can still win after the screening pass ------------------------------
-// One CTA per pair.  c1[h] = inliers among the first m1 = screen_len(M) correspondences, so
+// ---- winner-only: which hypotheses can still win ---------------------------------------------------------
+// Step 1: the first kWinnerChunk0 hypotheses are scored completely; if one of them exceeds 0.8 M the lowest such
+// index is the reference's answer and the pair is finished (ransac_early_kernel).  On clean data (most minimal
+// samples all-inlier) that is nearly every pair, at 128 / H of the full cost.
+// Step 2, for the other pairs, one CTA per pair (ransac_bound_kernel) over the hypotheses [kWinnerChunk0, H):
+// c1[h] = inliers among the first m1 = screen_len(M) correspondences, so
 // c1[h] <= count[h] <= ub[h] = c1[h] + (M - m1).  The kBoundTop hypotheses with the largest c1 are finished here
 // (float64, the rest of the correspondences) and give L = the largest COMPLETE count.  A hypothesis matters to
 // the reference's rule (first h above 0.8 M, else the lowest h among the maximum, homography.py:335-339) only if
@@ -259,11 +266,47 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
 // returns exactly the winner of the full evaluation.
 constexpr int kBoundThreads = 256;
 constexpr int kBoundTop = 8;
+constexpr int kWinnerChunk0 = 128;   // hypotheses scored to the end before anything else (winner-only mode)
 
+// After the first kWinnerChunk0 hypotheses were scored completely: the first of them above 0.8 M (if any) IS the
+// reference's answer — its loop stops there (homography.py:338-339) — and nothing else needs evaluating for this pair.
+// early[pair] = that index or -1; chunk_max[pair] = the largest complete count so far (a lower bound of the maximum).
+__global__ void __launch_bounds__(128) ransac_early_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ c_count,
+                                                           int H, int h_end, int32_t* __restrict__ early, int32_t* __restrict__ chunk_max) {
+  __shared__ int s_first, s_max;
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s_first = 0x7FFFFFFF, s_max = 0;
+  __syncthreads();
+  const double thr = 0.8 * (double)max(c_count[pair], 0);
+  int first = 0x7FFFFFFF, mx = 0;
+  for (int h = tid; h < h_end; h += blockDim.x) {
+    const int c = counts[(size_t)pair * H + h];
+    if ((double)c > thr) first = min(first, h);
+    mx = max(mx, c);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+    mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  }
+  if ((tid & 31) == 0) {
+    atomicMin(&s_first, first);
+    atomicMax(&s_max, mx);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    early[pair] = s_first == 0x7FFFFFFF ? -1 : s_first;
+    chunk_max[pair] = s_max;
+  }
+}
+
+// Hypotheses [h0, H) after the screening pass (see the header of this section); L also takes the complete counts of
+// the first chunk.
 __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
-    const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp, int32_t* __restrict__ counts,
-    int32_t* __restrict__ list, int32_t* __restrict__ n_list) {
+    const double* __restrict__ E, int H, int h0, double th2_all, const double* __restrict__ th2_pp, int32_t* __restrict__ counts,
+    int32_t* __restrict__ list, int32_t* __restrict__ n_list, const int32_t* __restrict__ early,
+    const int32_t* __restrict__ chunk_max) {
   __shared__ unsigned long long s_red[kBoundThreads / 32];
   __shared__ unsigned long long s_top[kBoundTop];
   __shared__ int s_cnt[kBoundTop];
@@ -274,7 +317,7 @@ __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
   int32_t* cnt = counts + (size_t)pair * H;
   const float4* cp = corr + c_off[pair];
   const double th2 = th2_pp ? th2_pp[pair] : th2_all;
-  if (M == m1) {   // nothing left to evaluate: every count is complete, nobody needs finishing
+  if (M == m1 || early[pair] >= 0 || h0 >= H) {   // nothing left to evaluate, or the answer is already known
     if (tid == 0) n_list[pair] = 0;
     return;
   }
@@ -283,7 +326,7 @@ __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
   unsigned long long last = ~0ull;
   for (int r = 0; r < kBoundTop; ++r) {
     unsigned long long best = 0ull;
-    for (int h = tid; h < H; h += kBoundThreads) {
+    for (int h = h0 + tid; h < H; h += kBoundThreads) {
       const unsigned long long key = ((unsigned long long)(uint32_t)cnt[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
       if (key < last && key > best) best = key;
     }
@@ -321,7 +364,7 @@ __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
   }
   __syncthreads();
   if (tid == 0) {
-    int L = 0;
+    int L = chunk_max[pair];                                   // complete counts of the first chunk
     for (int r = 0; r < kBoundTop; ++r) {
       if (s_top[r] == 0ull) break;
       const int h = (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull));
@@ -329,16 +372,16 @@ __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
       cnt[h] = full;                                           // complete
       L = max(L, full);
     }
-    const int early = (int)floor(0.8 * (double)M) + 1;         // smallest count with count > 0.8 * M (float64, as the reference compares)
-    s_need = min(L, early) - (M - m1);                         // survive iff c1[h] >= need
+    const int early_cnt = (int)floor(0.8 * (double)M) + 1;     // smallest count with count > 0.8 * M (float64, as the reference compares)
+    s_need = min(L, early_cnt) - (M - m1);                     // survive iff c1[h] >= need
   }
   __syncthreads();
   // ---- ordered compaction of the survivors (the finished ones excluded) ----
   const int need = s_need;
-  const int per = (H + kBoundThreads - 1) / kBoundThreads;
-  const int h0 = tid * per, h1 = min(H, h0 + per);
+  const int per = (H - h0 + kBoundThreads - 1) / kBoundThreads;
+  const int ha = h0 + tid * per, hb = min(H, ha + per);
   int mine = 0;
-  for (int h = h0; h < h1; ++h) {
+  for (int h = ha; h < hb; ++h) {
     bool done = false;
 #pragma unroll
     for (int r = 0; r < kBoundTop; ++r) done |= (s_top[r] != 0ull && (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull)) == h);
@@ -355,7 +398,7 @@ __global__ void __launch_bounds__(kBoundThreads) ransac_bound_kernel(
   int base = 0;
   for (int w = 0; w < warp; ++w) base += s_scan[w];
   int pos = base + incl - mine;
-  for (int h = h0; h < h1; ++h) {
+  for (int h = ha; h < hb; ++h) {
     bool done = false;
 #pragma unroll
     for (int r = 0; r < kBoundTop; ++r) done |= (s_top[r] != 0ull && (int)(0xFFFFFFFFu - (uint32_t)(s_top[r] & 0xFFFFFFFFull)) == h);
@@ -369,11 +412,13 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
     const int32_t* __restrict__ counts, const float4* __restrict__ corr, const int32_t* __restrict__ c_off,
     const int32_t* __restrict__ c_count, const double* __restrict__ E, int H, double th2_all,
     const double* __restrict__ th2_pp, int32_t* __restrict__ best_h, int32_t* __restrict__ best_count,
-    uint8_t* __restrict__ mask) {
+    uint8_t* __restrict__ mask, const int32_t* __restrict__ early_in, int h_chunk) {
   __shared__ int s_early;
   __shared__ unsigned long long s_best;
   __shared__ int s_cnt;
   const int pair = blockIdx.x, tid = threadIdx.x;
+  const int H_all = H;
+  if (early_in && early_in[pair] >= 0) H = min(H, h_chunk);   // winner-only: only the first chunk was evaluated for this pair
   const int M = max(c_count[pair], 0);   // a negative count is the selection kernel's overflow flag: no model
   if (tid == 0) {
     s_early = 0x7FFFFFFF;
@@ -385,7 +430,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
   int early = 0x7FFFFFFF;
   unsigned long long bestk = 0ull;
   for (int h = tid; h < H; h += blockDim.x) {
-    const int c = counts[(size_t)pair * H + h];
+    const int c = counts[(size_t)pair * H_all + h];
     if ((double)c > early_thr) early = min(early, h);
     // larger count wins; among equal counts the lower h (first strict improvement) wins
     const unsigned long long k = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
@@ -403,7 +448,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
   int mine = 0;
   if (win >= 0) {
     double e[9];
-    const double* ep = E + ((size_t)pair * H + win) * 9;
+    const double* ep = E + ((size_t)pair * H_all + win) * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) e[k] = ep[k];
     const double th2 = th2_pp ? th2_pp[pair] : th2_all;
@@ -578,7 +623,7 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
       B2S_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * H, st));
       grid.z = zs;
     }
-    ransac_score_hybrid_kernel<0><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr);
+    ransac_score_hybrid_kernel<0><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr, 0, H, nullptr);
   } else if (precision == 6464)
     ransac_score_kernel<double><<<grid, kScoreThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr);
   else
@@ -590,7 +635,8 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
 
 size_t b2s_ransac_winner_workspace_bytes(int n_pairs, int H) {
   if (n_pairs <= 0 || H <= 0) return 0;
-  return sizeof(int32_t) * ((size_t)n_pairs * H * 2 + (size_t)n_pairs) + 256;   // counts | survivor list | survivors per pair
+  // counts | survivor list | survivors per pair | early index per pair | first-chunk maximum per pair
+  return sizeof(int32_t) * ((size_t)n_pairs * H * 2 + 3 * (size_t)n_pairs) + 256;
 }
 
 int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
@@ -606,20 +652,38 @@ int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int
               "winner-only scoring needs b2s_ransac_winner_workspace_bytes(n_pairs, H) bytes, 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* c4 = reinterpret_cast<const float4*>(corr);
-  int32_t* counts = counts_out ? counts_out : static_cast<int32_t*>(workspace);
-  int32_t* list = static_cast<int32_t*>(workspace) + (size_t)n_pairs * H;
+  int32_t* ws = static_cast<int32_t*>(workspace);
+  int32_t* counts = counts_out ? counts_out : ws;
+  int32_t* list = ws + (size_t)n_pairs * H;
   int32_t* n_list = n_finished_out ? n_finished_out : list + (size_t)n_pairs * H;
+  int32_t* early = list + (size_t)n_pairs * H + n_pairs;
+  int32_t* chunk_max = early + n_pairs;
+  const int h0 = H < kWinnerChunk0 ? H : kWinnerChunk0;
   if (H > 0) {
-    dim3 grid((H + kScoreHThreads - 1) / kScoreHThreads, n_pairs);
-    ransac_score_hybrid_kernel<1><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr);
+    if (counts_out) B2S_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int32_t) * (size_t)n_pairs * H, st));   // unevaluated entries read 0
+    // 1. the first chunk to the end, and whether it already holds the answer
+    dim3 g0((h0 + kScoreHThreads - 1) / kScoreHThreads, n_pairs);
+    ransac_score_hybrid_kernel<0><<<g0, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr, 0, h0, nullptr);
     B2S_CUDA(cudaGetLastError());
-    ransac_bound_kernel<<<n_pairs, kBoundThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, list, n_list);
+    ransac_early_kernel<<<n_pairs, 128, 0, st>>>(counts, c_count, H, h0, early, chunk_max);
     B2S_CUDA(cudaGetLastError());
-    ransac_score_hybrid_kernel<2><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, list, n_list);
-    B2S_CUDA(cudaGetLastError());
-    note_launch(3);
+    note_launch(2);
+    // 2. everything else: screen, bound, finish (pairs whose answer is known skip all three)
+    if (H > h0) {
+      dim3 grid((H - h0 + kScoreHThreads - 1) / kScoreHThreads, n_pairs);
+      ransac_score_hybrid_kernel<1><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, nullptr, nullptr, h0, H, early);
+      B2S_CUDA(cudaGetLastError());
+      ransac_bound_kernel<<<n_pairs, kBoundThreads, 0, st>>>(c4, c_off, c_count, E, H, h0, th2, th2_per_pair, counts, list, n_list, early, chunk_max);
+      B2S_CUDA(cudaGetLastError());
+      ransac_score_hybrid_kernel<2><<<grid, kScoreHThreads, 0, st>>>(c4, c_off, c_count, E, H, th2, th2_per_pair, counts, list, n_list, 0, H, early);
+      B2S_CUDA(cudaGetLastError());
+      note_launch(3);
+    } else if (n_finished_out) {
+      B2S_CUDA(cudaMemsetAsync(n_finished_out, 0, sizeof(int32_t) * (size_t)n_pairs, st));
+    }
   }
-  ransac_select_kernel<<<n_pairs, 256, 0, st>>>(counts, c4, c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count, inlier_mask);
+  ransac_select_kernel<<<n_pairs, 256, 0, st>>>(counts, c4, c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count, inlier_mask,
+                                                H > 0 ? early : nullptr, h0);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;
@@ -634,7 +698,7 @@ int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c
   if (n_pairs == 0) return B2S_OK;
   ransac_select_kernel<<<n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       counts, reinterpret_cast<const float4*>(corr), c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count,
-      inlier_mask);
+      inlier_mask, nullptr, 0);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;
