@@ -615,7 +615,8 @@ def run_config2(env, a):
 
     def step_body():
         for i in range(a.sub_batches):
-            sf.step(batches[i % W])
+            sf.step(batches[i % W])          # the all-gather of launch set i runs under the kernels of launch set i + 1
+        sf.wait()
     step, launches, graphed = _capture(env, step_body, use_graph=not a.no_graph)
     clocks = Clocks(env.local)
     if rank == 0:
@@ -657,6 +658,7 @@ def run_config2(env, a):
     def step_pose():
         for i in range(a.sub_batches):
             sfp.step(batches[i % W])
+        sfp.wait()
     step_p, _, _ = _capture(env, step_pose, use_graph=not a.no_graph)
     ms_p = env.timed(step_p, max(3, a.steps // 2), 2)
     value_pose = pairs_per_step * len(ms_p) / (env.max_over_ranks(float(np.sum(ms_p))) * 1e-3)
@@ -667,6 +669,7 @@ def run_config2(env, a):
     def step_winner():
         for i in range(a.sub_batches):
             sfw.step(batches[i % W])
+        sfw.wait()
     step_w, launches_w, _ = _capture(env, step_winner, use_graph=not a.no_graph)
     ms_w = env.timed(step_w, max(3, a.steps // 2), 2)
     value_winner = pairs_per_step * len(ms_w) / (env.max_over_ranks(float(np.sum(ms_w))) * 1e-3)
@@ -834,6 +837,7 @@ def run_config3(env, a, peaks=None, brief=False):
     def step_body():
         for i in range(a.sub_batches):
             sf.step(batches[i % W])
+        sf.wait()
     step, launches, graphed = _capture(env, step_body, use_graph=not a.no_graph)
     clocks = Clocks(env.local)
     if rank == 0 and not brief:

@@ -103,13 +103,15 @@ class RecordGather:
     def n_local(self) -> int:
         return self.hi - self.lo
 
-    def all_gather(self):
-        """Enqueue the collective on the current stream (capturable into a CUDA graph with NCCL)."""
+    def all_gather(self, async_op: bool = False):
+        """Enqueue the collective behind the current stream's work (capturable into a CUDA graph with NCCL).
+        async_op=True returns the work handle instead of making the current stream wait for the collective: the
+        caller's next kernels then overlap it, and `handle.wait()` orders whatever reads or rewrites the buffer."""
         if self.world > 1:
             import torch.distributed as dist
 
-            dist.all_gather_into_tensor(self.buf.view(-1), self.local.reshape(-1), group=self.group)
-        return self.buf
+            return dist.all_gather_into_tensor(self.buf.view(-1), self.local.reshape(-1), group=self.group, async_op=async_op)
+        return None
 
     def ordered(self):
         """[n_items, width] in pair order (a copy; padding rows of short shards dropped)."""
@@ -135,7 +137,9 @@ class ShardedFrontend:
     issued eagerly behind them (``gather_in_graph`` says which).  After a step every rank holds every pair's
     record (``records()`` -> device uint8 [n_pairs_global, record_bytes])."""
 
-    def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None):
+    def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None, n_buffers: int = 2):
+        """n_buffers gather buffers are used in turn and the all-gather is asynchronous: the collective of launch set
+        k runs under the kernels of launch set k + 1 (they do not depend on it); `wait()` joins what is outstanding."""
         from . import _capi
         from .frontend import Frontend, record_bytes
 
@@ -146,8 +150,12 @@ class ShardedFrontend:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fe = Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant)
         self.rec_bytes = record_bytes(cfg.max_matches)
-        self.gather = RecordGather(n_pairs_global, self.rec_bytes, dtype=torch.uint8, device=self.dev, group=group)
-        self.gather.buf.view(torch.int32).reshape(self.gather.world, self.gather.cap, -1)[:, :, 3] = -1   # padding slots: pair id -1
+        self.gathers = [RecordGather(n_pairs_global, self.rec_bytes, dtype=torch.uint8, device=self.dev, group=group)
+                        for _ in range(max(1, n_buffers))]
+        for g in self.gathers:
+            g.buf.view(torch.int32).reshape(g.world, g.cap, -1)[:, :, 3] = -1   # padding slots: pair id -1
+        self.gather = self.gathers[0]                  # the buffer of the most recent step
+        self._works, self._k = [None] * len(self.gathers), 0
         self.lo, self.hi, self.world, self.rank = self.gather.lo, self.gather.hi, self.gather.world, self.gather.rank
         self._graph, self._batch, self.res = None, None, None
         self.gather_in_graph = False
@@ -155,30 +163,56 @@ class ShardedFrontend:
     def step(self, batch, K=None):
         if batch.n_pairs != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns pairs [{self.lo}, {self.hi}) but the batch has {batch.n_pairs}")
-        self.res = self.fe.run(batch, K=K, records=self.gather.local[: batch.n_pairs], pair_id0=self.lo)
-        self.gather.all_gather()
+        i = self._k % len(self.gathers)
+        self._k += 1
+        g = self.gathers[i]
+        if self._works[i] is not None:             # the collective that last read this buffer must be done before it is rewritten
+            self._works[i].wait()
+            self._works[i] = None
+        self.res = self.fe.run(batch, K=K, records=g.local[: batch.n_pairs], pair_id0=self.lo)
+        self._works[i] = g.all_gather(async_op=True)
+        self.gather = g
         return self.res
 
-    def capture(self, batch, K=None, collective_in_graph: bool = True):
-        """One eager step (lazy init, workspaces, NCCL warm-up), then the capture."""
+    def wait(self):
+        """Order the current stream behind every outstanding all-gather (end of a step, before the records are read)."""
+        for i, w in enumerate(self._works):
+            if w is not None:
+                w.wait()
+                self._works[i] = None
+
+    def capture(self, batches, K=None, collective_in_graph: bool = True):
+        """One eager pass (lazy init, workspaces, NCCL warm-up), then the capture of step(b) for every b of `batches`
+        (one PairBatch or a list: a step of several launch sets) followed by wait()."""
         import torch
 
-        self.step(batch, K)
+        batches = batches if isinstance(batches, (list, tuple)) else [batches]
+
+        def body():
+            for b in batches:
+                self.step(b, K)
+            self.wait()
+        body()
         torch.cuda.synchronize()
-        self._batch, self._K = batch, K
+        self._k = 0
         g = torch.cuda.CUDAGraph()
         self.gather_in_graph = False
         if collective_in_graph and self.world > 1:
             try:
                 with torch.cuda.graph(g):
-                    self.step(batch, K)
+                    body()
                 self.gather_in_graph = True
             except Exception:                      # NCCL / torch build that cannot capture the collective
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
         if not self.gather_in_graph:
+            self._eager_gathers = []
             with torch.cuda.graph(g):
-                self.res = self.fe.run(batch, K=K, records=self.gather.local[: batch.n_pairs], pair_id0=self.lo)
+                for j, b in enumerate(batches):
+                    gg = self.gathers[j % len(self.gathers)]
+                    self.res = self.fe.run(b, K=K, records=gg.local[: b.n_pairs], pair_id0=self.lo)
+                    self.gather = gg
+            self._eager_gathers = [self.gather]     # only the last launch set's records can be gathered behind the graph
         self._graph = g
         torch.cuda.synchronize()
         return self.gather_in_graph
@@ -186,7 +220,8 @@ class ShardedFrontend:
     def replay(self):
         self._graph.replay()
         if not self.gather_in_graph:
-            self.gather.all_gather()
+            for gg in self._eager_gathers:
+                gg.all_gather()
         return self.res
 
     def records(self):
@@ -194,6 +229,7 @@ class ShardedFrontend:
 
     def close(self):
         """Release the captured graph (it holds the NCCL all-gather node: see shutdown_process_group)."""
+        self.wait()
         self._graph = None
 
 

@@ -46,6 +46,7 @@ if a.config == 3:
     print(f"[rank {rank}] captured, collective_in_graph={in_graph}", file=sys.stderr, flush=True)
     for _ in range(2):
         sf.replay()
+    sf.wait()
     torch.cuda.synchronize()
     u = unpack_records(sf.records().cpu().numpy(), S)
     out = {k: v for k, v in u.items()}
