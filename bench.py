@@ -410,6 +410,26 @@ class Env:
             shutdown_process_group()
 
 
+def sharded_step(env, sf, batch_list, use_graph=True):
+    """One step = the launch sets of `batch_list` through the library's ShardedFrontend: one eager pass (lazy init;
+    counts the library's launches), then the whole batch — kernels, record kernels and the collective — as ONE CUDA
+    graph.  -> (step callable, launches per step, graphed)."""
+    torch = env.torch
+    l0 = env.lib.b2s_launch_count()
+    for b in batch_list:
+        sf.step(b)
+    sf.flush()
+    torch.cuda.synchronize()
+    launches = int(env.lib.b2s_launch_count() - l0)
+    if not use_graph:
+        def eager():
+            for b in batch_list:
+                sf.step(b)
+        return eager, launches, False
+    sf.capture(batch_list)
+    return sf.replay, launches, True
+
+
 def _capture(env, fn, use_graph=True):
     """Run fn once eagerly (lazy init; counts the library's launches), then capture it into ONE CUDA graph.
     -> (replay callable, launches per call)."""
@@ -611,13 +631,13 @@ def run_config2(env, a):
 
     # One step = `sub_batches` launch sets (windows of P consecutive pairs, W distinct windows cycled) through the
     # library's pair-sharded entry: kernels + record kernel + (N > 1) the in-place all-gather, ONE CUDA graph.
-    sf = ShardedFrontend(cfg, world * P, variant=env.variant)                   # weak scaling: P pairs per rank per launch set
+    # weak scaling: P pairs per rank per launch set; the records of a step's launch sets leave in ONE all-gather
+    sf = ShardedFrontend(cfg, world * P, variant=env.variant, sets_per_gather=a.sub_batches)
 
-    def step_body():
-        for i in range(a.sub_batches):
-            sf.step(batches[i % W])          # the all-gather of launch set i runs under the kernels of launch set i + 1
-        sf.wait()
-    step, launches, graphed = _capture(env, step_body, use_graph=not a.no_graph)
+    batch_list = [batches[i % W] for i in range(a.sub_batches)]
+    # steady state: the graph of a step holds the all-gather of the PREVIOUS step's records (it runs under this step's
+    # first RANSAC kernels), so every timed step contains exactly one collective
+    step, launches, graphed = sharded_step(env, sf, batch_list, use_graph=not a.no_graph)
     clocks = Clocks(env.local)
     if rank == 0:
         clocks.start()
@@ -653,25 +673,20 @@ def run_config2(env, a):
 
     # ---- the same step, additionally refitting E on the inliers and recovering (R, t) (K7) into the records ----
     import dataclasses
-    sfp = ShardedFrontend(dataclasses.replace(cfg, with_pose=True), world * P, variant=env.variant)
+    sfp = ShardedFrontend(dataclasses.replace(cfg, with_pose=True), world * P, variant=env.variant, sets_per_gather=a.sub_batches)
 
-    def step_pose():
-        for i in range(a.sub_batches):
-            sfp.step(batches[i % W])
-        sfp.wait()
-    step_p, _, _ = _capture(env, step_pose, use_graph=not a.no_graph)
+    step_p, _, _ = sharded_step(env, sfp, batch_list, use_graph=not a.no_graph)
     ms_p = env.timed(step_p, max(3, a.steps // 2), 2)
+    sfp.flush()
     value_pose = pairs_per_step * len(ms_p) / (env.max_over_ranks(float(np.sum(ms_p))) * 1e-3)
     del sfp
     # ---- the same step with winner-only scoring: identical winner / inlier mask, hypotheses that cannot win abandoned early ----
-    sfw = ShardedFrontend(dataclasses.replace(cfg, winner_only=True), world * P, variant=env.variant)
+    sfw = ShardedFrontend(dataclasses.replace(cfg, winner_only=True), world * P, variant=env.variant, sets_per_gather=a.sub_batches)
 
-    def step_winner():
-        for i in range(a.sub_batches):
-            sfw.step(batches[i % W])
-        sfw.wait()
-    step_w, launches_w, _ = _capture(env, step_winner, use_graph=not a.no_graph)
+    step_w, launches_w, _ = sharded_step(env, sfw, batch_list, use_graph=not a.no_graph)
     ms_w = env.timed(step_w, max(3, a.steps // 2), 2)
+    sfw.flush()
+    sf.flush()
     value_winner = pairs_per_step * len(ms_w) / (env.max_over_ranks(float(np.sum(ms_w))) * 1e-3)
     same_winner = bool(torch.equal(sfw.res.best_h, sf.res.best_h) and torch.equal(sfw.res.best_count, sf.res.best_count)
                        and torch.equal(sfw.res.inlier_mask, sf.res.inlier_mask))
@@ -781,7 +796,10 @@ def run_config2(env, a):
              "value_with_pose": value_pose,
              "value_with_pose_note": "same step + n-point refit of E on the winner's inliers + decomposition / cheirality vote (K7), R | t in the records; "
                                      "outside the metric's unit (SURVEY 8d), reported beside it",
-             "record_bytes_per_pair": sf.rec_bytes,
+             "record_bytes_per_pair": sf.rec_bytes, "collectives_per_step": 1 if world > 1 else 0,
+             "collective_schedule": ("the all-gather of step s is a node of step s + 1's graph, started after its first selection kernel and joined before "
+                                     "its first record kernel (under the 8-point / scoring kernels)") if (world > 1 and sf.pipelined) else ("after the step's last launch set" if world > 1 else None),
+             "gather_bytes_per_step_per_rank": int(sf.rec_bytes * P * a.sub_batches),
              "popc_kernel_config": dict(zip(("csa_level", "rows_per_thread", "warps"), _getcfg(lib)))}
     line = _base_line(env, a, value, total_ms, "weak", clk, roof, e2e, stages, launches, extra)
     if a.sweep:
@@ -825,7 +843,7 @@ def run_config3(env, a, peaks=None, brief=False):
     rank, world, dev = env.rank, env.world, env.dev
     n_glob, W = a.pairs, min(2 if brief else DISTINCT_WINDOWS, a.sub_batches)
     cfg = FrontendConfig(hypotheses=a.hyps, max_matches=500, threshold=0.01, precision=64, seed=1337, scoring=a.scoring)
-    sf = ShardedFrontend(cfg, n_glob, variant=env.variant)                       # strong scaling: the 256 pairs are split over the ranks
+    sf = ShardedFrontend(cfg, n_glob, variant=env.variant, sets_per_gather=a.sub_batches)   # strong scaling: the 256 pairs are split over the ranks
     lo, hi = sf.lo, sf.hi
     host = []
     for w in range(W):                                                            # every rank generates the same batch and keeps its block
@@ -834,15 +852,12 @@ def run_config3(env, a, peaks=None, brief=False):
     batches = [PairBatch.from_host(*h) for h in host]
     torch.cuda.synchronize()
 
-    def step_body():
-        for i in range(a.sub_batches):
-            sf.step(batches[i % W])
-        sf.wait()
-    step, launches, graphed = _capture(env, step_body, use_graph=not a.no_graph)
+    step, launches, graphed = sharded_step(env, sf, [batches[i % W] for i in range(a.sub_batches)], use_graph=not a.no_graph)
     clocks = Clocks(env.local)
     if rank == 0 and not brief:
         clocks.start()
     ms = env.timed(step, a.steps, a.warmup)
+    sf.flush()
     total_ms = env.max_over_ranks(float(np.sum(ms)))
     value = n_glob * a.sub_batches * a.steps / (total_ms * 1e-3)
     if peaks is None and rank == 0:
@@ -853,7 +868,7 @@ def run_config3(env, a, peaks=None, brief=False):
     depth = max(1, a.e2e_depth)
     pipe = PairPipeline(hi - lo, a.nfeat, a.nfeat, cfg, variant=env.variant, depth=depth, device=dev, use_graph=not a.no_graph)
     if world > 1:
-        gathered = [torch.empty((world, sf.gather.cap, pipe.rec_bytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        gathered = [torch.empty((world, sf.cap, pipe.rec_bytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
         for sl, g in zip(pipe.slots, gathered):
             sl["rec_dev"] = g[rank][: hi - lo]
             sl["gathered"] = g

@@ -682,15 +682,21 @@ class Frontend:
         return self.ransac.score(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, precision=c.precision,
                                  max_m=sel.stride or b.max_nq)
 
-    def run(self, b: PairBatch, K=None, samples=None, records=None, pair_id0: int = 0) -> FrontendResult:
+    def run(self, b: PairBatch, K=None, samples=None, records=None, pair_id0: int = 0,
+            after_select=None, before_records=None) -> FrontendResult:
         """records: optional device uint8 [n_pairs, record_bytes(max_matches)] — e.g. this rank's slice of the
         all-gather buffer, or the staging buffer of the step's one device->host copy; the last kernel of the
-        step writes every pair's result record into it (pair ids pair_id0 + p)."""
+        step writes every pair's result record into it (pair ids pair_id0 + p).
+        after_select / before_records: optional callables run (on the current stream) after the selection kernel and
+        before the record kernel — where ShardedFrontend starts and joins the collective of the PREVIOUS batch, so
+        that it overlaps the multi-wave RANSAC kernels and never the persistent one-CTA-per-SM Hamming kernel."""
         c = self.cfg
         keys = self.matcher.knn2(b)
         sel = self.matcher.select(b, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
                                   sort_by_distance=True, max_matches=c.max_matches, with_corr=True,
                                   compact=True)
+        if after_select is not None:
+            after_select()
         E = self.ransac.hypotheses(sel.corr, sel.c_off, sel.count, b.n_pairs, c.hypotheses,
                                    samples=samples, seed=c.seed, K=K, pair_id0=pair_id0)
         th2 = c.threshold ** 2
@@ -706,6 +712,8 @@ class Frontend:
                 self.pose = PoseRecovery()
             res.E_refit, res.R, res.t, res.votes = self.pose.recover(sel.corr, sel.c_off, sel.count, b.n_pairs,
                                                                       sel.stride or b.max_nq, mask=mask, K=K)
+        if before_records is not None:
+            before_records()
         if records is not None:
             pack_records(records, sel, best_h, best_c, mask, res.R, res.t, n_records=b.n_pairs, pair_id0=pair_id0)
             res.records = records

@@ -131,15 +131,27 @@ class ShardedFrontend:
 
     ``n_pairs_global`` pairs are split with ``shard_bounds``; the caller builds the PairBatch of ITS pairs
     (``self.lo .. self.hi``).  ``step(batch)`` runs match -> select -> hypotheses -> score -> winner (-> refit ->
-    decomposition when cfg.with_pose), the record kernel writes into this rank's slice of the gather buffer, and the all-gather
-    follows on the same stream.  ``capture(batch)`` records exactly that — collective included — into one CUDA
-    graph (``replay()``); if the NCCL build cannot be captured the kernels are replayed and the collective is
-    issued eagerly behind them (``gather_in_graph`` says which).  After a step every rank holds every pair's
-    record (``records()`` -> device uint8 [n_pairs_global, record_bytes])."""
+    decomposition when cfg.with_pose) and the record kernel writes this rank's records into the send buffer.
+    A batch may be processed as ``sets_per_gather`` launch sets (sub-batches that keep every kernel's grid at a few
+    waves); its records leave in ONE ``all_gather_into_tensor``.
 
-    def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None, n_buffers: int = 2):
-        """n_buffers gather buffers are used in turn and the all-gather is asynchronous: the collective of launch set
-        k runs under the kernels of launch set k + 1 (they do not depend on it); `wait()` joins what is outstanding."""
+    ``pipelined=True`` (default): the collective of batch k is issued inside the first launch set of batch k + 1 —
+    started after that set's selection kernel, joined before its record kernel — so it runs under the multi-wave
+    RANSAC kernels (8-point, scoring, winner) and is off the critical path; ``flush()`` gathers the last batch, and
+    ``records()`` is then complete.  ``pipelined=False``: the collective follows the batch's last launch set on the
+    same stream.  Measured at 8 GPUs against 1 GPU on the same box (profiles/r02_scale.md): a collective per launch set
+    0.912, the same overlapped with the next set's kernels 0.938 (the NCCL kernel takes SMs away from the persistent
+    one-CTA-per-SM Hamming kernel that follows it, whose late CTAs then finish late), one collective per batch 0.969,
+    pipelined under the RANSAC kernels: see that file.
+
+    ``capture(batches)`` records a whole batch — collective included — into ONE CUDA graph (``replay()``); if the
+    NCCL build cannot be captured the kernels are replayed and the collective is issued eagerly (``gather_in_graph``
+    says which).  ``records()`` -> device uint8 [sets_per_gather, n_pairs_global, record_bytes]."""
+
+    def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None, sets_per_gather: int = 1,
+                 pipelined: bool = True):
+        import os
+
         from . import _capi
         from .frontend import Frontend, record_bytes
 
@@ -150,54 +162,88 @@ class ShardedFrontend:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fe = Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant)
         self.rec_bytes = record_bytes(cfg.max_matches)
-        self.gathers = [RecordGather(n_pairs_global, self.rec_bytes, dtype=torch.uint8, device=self.dev, group=group)
-                        for _ in range(max(1, n_buffers))]
-        for g in self.gathers:
-            g.buf.view(torch.int32).reshape(g.world, g.cap, -1)[:, :, 3] = -1   # padding slots: pair id -1
-        self.gather = self.gathers[0]                  # the buffer of the most recent step
-        self._works, self._k = [None] * len(self.gathers), 0
-        self.lo, self.hi, self.world, self.rank = self.gather.lo, self.gather.hi, self.gather.world, self.gather.rank
-        self._graph, self._batch, self.res = None, None, None
+        self.sets = max(1, int(sets_per_gather))
+        self.n_pairs_global = int(n_pairs_global)
+        self.world, self.group = _world(group), group
+        self.cap = shard_capacity(self.n_pairs_global, self.world)
+        # send = this rank's records of the batch in progress [sets * cap][record]; recv = every rank's records of
+        # the last gathered batch [world][sets * cap][record]
+        self.gather = RecordGather(self.world * self.sets * self.cap, self.rec_bytes, dtype=torch.uint8, device=self.dev, group=group)
+        self.rank = self.gather.rank
+        self.gather.buf.view(torch.int32).reshape(self.world, self.gather.cap, -1)[:, :, 3] = -1   # padding slots: pair id -1
+        self.pipelined = bool(pipelined) and os.environ.get("B2S_GATHER", "pipelined") != "sync"
+        if self.pipelined and self.world > 1:
+            self.send = torch.zeros((self.sets * self.cap, self.rec_bytes), dtype=torch.uint8, device=self.dev)
+            self.send.view(torch.int32)[:, 3] = -1
+        else:
+            self.send = self.gather.local               # in-place: the send slice of the gather buffer itself
+        self.lo, self.hi = shard_bounds(self.n_pairs_global, self.rank, self.world)
+        self._work, self._k, self._pending = None, 0, False
+        self._graph, self.res = None, None
         self.gather_in_graph = False
+
+    # ---- the collective ------------------------------------------------------------------------------------
+    def _start_gather(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            self._work = dist.all_gather_into_tensor(self.gather.buf.view(-1), self.send.reshape(-1), group=self.group, async_op=True)
+
+    def _join_gather(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
 
     def step(self, batch, K=None):
         if batch.n_pairs != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns pairs [{self.lo}, {self.hi}) but the batch has {batch.n_pairs}")
-        i = self._k % len(self.gathers)
+        j = self._k % self.sets
         self._k += 1
-        g = self.gathers[i]
-        if self._works[i] is not None:             # the collective that last read this buffer must be done before it is rewritten
-            self._works[i].wait()
-            self._works[i] = None
-        self.res = self.fe.run(batch, K=K, records=g.local[: batch.n_pairs], pair_id0=self.lo)
-        self._works[i] = g.all_gather(async_op=True)
-        self.gather = g
+        rows = self.send[j * self.cap: j * self.cap + batch.n_pairs]
+        first = j == 0 and self.pipelined and self.world > 1 and self._pending
+        # pipelined: the previous batch's records (still in `send`) leave while this set's RANSAC kernels run; the
+        # record kernel of this set, which overwrites the first rows of `send`, waits for the collective
+        self.res = self.fe.run(batch, K=K, records=rows, pair_id0=self.lo,
+                               after_select=self._start_gather if first else None,
+                               before_records=self._join_gather if first else None)
+        if j == self.sets - 1:                      # the batch's last launch set
+            if self.pipelined and self.world > 1:
+                self._pending = True                # gathered inside the next batch (or by flush())
+            else:
+                self.gather.all_gather()
         return self.res
 
-    def wait(self):
-        """Order the current stream behind every outstanding all-gather (end of a step, before the records are read)."""
-        for i, w in enumerate(self._works):
-            if w is not None:
-                w.wait()
-                self._works[i] = None
+    def flush(self):
+        """Gather the last batch's records (pipelined mode) and order the current stream behind the collective."""
+        if self._pending:
+            self._start_gather()
+            self._pending = False
+        self._join_gather()
+
+    wait = flush
 
     def capture(self, batches, K=None, collective_in_graph: bool = True):
         """One eager pass (lazy init, workspaces, NCCL warm-up), then the capture of step(b) for every b of `batches`
-        (one PairBatch or a list: a step of several launch sets) followed by wait()."""
+        (one PairBatch or a list of sets_per_gather launch sets = one batch).  In pipelined mode the graph holds the
+        collective of the PREVIOUS replay's batch (steady state: one collective per replay); call flush() after the
+        last replay."""
         import torch
 
         batches = batches if isinstance(batches, (list, tuple)) else [batches]
+        if len(batches) != self.sets:
+            raise ValueError("capture: pass exactly sets_per_gather launch sets (one batch)")
 
         def body():
             for b in batches:
                 self.step(b, K)
-            self.wait()
-        body()
-        torch.cuda.synchronize()
         self._k = 0
+        body()
+        self.flush()
+        torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         self.gather_in_graph = False
         if collective_in_graph and self.world > 1:
+            self._k, self._pending = 0, self.pipelined
             try:
                 with torch.cuda.graph(g):
                     body()
@@ -205,32 +251,56 @@ class ShardedFrontend:
             except Exception:                      # NCCL / torch build that cannot capture the collective
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                self._work = None
         if not self.gather_in_graph:
-            self._eager_gathers = []
             with torch.cuda.graph(g):
                 for j, b in enumerate(batches):
-                    gg = self.gathers[j % len(self.gathers)]
-                    self.res = self.fe.run(b, K=K, records=gg.local[: b.n_pairs], pair_id0=self.lo)
-                    self.gather = gg
-            self._eager_gathers = [self.gather]     # only the last launch set's records can be gathered behind the graph
+                    self.res = self.fe.run(b, K=K, records=self.send[j * self.cap: j * self.cap + b.n_pairs], pair_id0=self.lo)
+        self._k = 0
+        self._pending = self.pipelined and self.world > 1     # the eager pass left a complete batch in `send`
         self._graph = g
         torch.cuda.synchronize()
         return self.gather_in_graph
 
     def replay(self):
         self._graph.replay()
-        if not self.gather_in_graph:
-            for gg in self._eager_gathers:
-                gg.all_gather()
+        if self.world > 1:
+            if not self.gather_in_graph:
+                self._start_gather()                # eager, behind the graph
+                self._join_gather()
+                self._pending = False
+            elif self.pipelined:
+                self._pending = True                # this replay's batch is gathered by the next replay, or by flush()
         return self.res
 
     def records(self):
-        return self.gather.ordered()
+        """[sets_per_gather, n_pairs_global, record_bytes] in pair order (padding rows of short shards dropped); in
+        pipelined mode call flush() first."""
+        import torch
+
+        v = self.gather.buf.view(self.world, self.sets, self.cap, self.rec_bytes)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.n_pairs_global, r, self.world)
+            parts.append(v[r, :, : hi - lo])
+        return torch.cat(parts, dim=1)
 
     def close(self):
         """Release the captured graph (it holds the NCCL all-gather node: see shutdown_process_group)."""
-        self.wait()
+        self._work = None
         self._graph = None
+
+
+def _dist_on(group=None) -> bool:
+    import torch.distributed as dist
+
+    return dist.is_available() and dist.is_initialized()
+
+
+def _world(group=None) -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size(group) if _dist_on(group) else 1
 
 
 class ShardedSweep:

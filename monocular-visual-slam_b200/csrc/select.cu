@@ -38,27 +38,31 @@ struct SelectParams {
   int n_sort;  // power of two >= max_nq
 };
 
-// Distances are integers 0..256, so the reference's stable sort by distance is a COUNTING sort:
-// histogram of the survivors' distances, exclusive prefix sum, and a stable placement pass in which
-// one warp walks the query rows 32 at a time — __match_any_sync groups the lanes of equal distance,
-// the lowest lane of a group advances that distance's cursor, the others take the slots behind it in
-// lane (= query index) order.  2000 queries: 63 short iterations instead of the 66 block-wide
-// barrier passes of a 2048-key bitonic sort (37 -> ~10 us per 296 pairs).  sort_by_distance = 0 is the
-// same pass with a single bin (ascending query index).
+// Distances are integers 0..256, so the reference's stable sort by distance is a COUNTING sort.  Every warp of the
+// CTA owns a contiguous segment of the query rows: (1) it histograms the distances of its segment's survivors into
+// its own row of a [warps][bins] table, (2) the table is turned into output cursors — bins ascending, within a bin
+// the warps (= row segments) ascending — and (3) every warp places its segment 32 rows at a time: __match_any_sync
+// groups the lanes of equal distance, the lowest lane of a group advances that distance's cursor, the others take
+// the slots behind it in lane (= query index) order.  Ties therefore keep ascending queryIdx exactly like the
+// reference's stable list.sort.  (Round 1 placed with ONE warp: 63 dependent iterations for 2000 rows, 313 for the
+// 10 000 rows of BASELINE config #4 — 0.10 ms, half of a lone 10k x 10k pair.)  sort_by_distance = 0 is the same
+// with a single bin (ascending query index).
 constexpr int kSelBins = 257;
+constexpr int kSelBinsPad = 264;   // row stride of the per-warp table
 
 __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams p, const RatioLut lut) {
-  extern __shared__ uint16_t s_sel[];       // [n_sort] distance (0xFFFF = dropped) | [n_sort] query index by output position
-  __shared__ int s_hist[kSelBins + 31];
+  extern __shared__ uint16_t s_sel[];       // [n_sort] distance (0xFFFF = dropped) | [n_sort] query index by output position | int [warps][kSelBinsPad]
+  __shared__ int s_tot[kSelBinsPad + 32];   // survivors per bin, then the bin's first output position
   __shared__ int s_count;
   uint16_t* s_d = s_sel;
   uint16_t* s_sorted = s_sel + p.n_sort;
+  int* s_hist = reinterpret_cast<int*>(s_sel + 2 * p.n_sort);
   const int pair = blockIdx.x;
   const int qo = p.q_off[pair];
   const int nq = p.q_off[pair + 1] - qo;
   const int to = p.t_off[pair];
   const int ob = p.out_stride > 0 ? pair * p.out_stride : qo;  // output base
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   if (nq > p.n_sort) {  // caller's max_nq was too small for this pair: flag it, never overrun smem
     if (tid == 0) {
       p.out_count[pair] = -1;
@@ -66,11 +70,15 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
     }
     return;
   }
-  for (int b = tid; b < kSelBins + 31; b += nthr) s_hist[b] = 0;
+  for (int b = tid; b < nwarps * kSelBinsPad; b += nthr) s_hist[b] = 0;
+  for (int b = tid; b < kSelBinsPad + 32; b += nthr) s_tot[b] = 0;
   __syncthreads();
 
-  // ---- survivors and the histogram of their distances ----
-  for (int i = tid; i < nq; i += nthr) {
+  // ---- (1) survivors and the histogram of their distances, per warp segment ----
+  const int seg = (((nq + nwarps - 1) / nwarps) + 31) & ~31;      // rows per warp, a multiple of 32
+  const int r0 = warp * seg, r1 = min(nq, r0 + seg);
+  int* my_hist = s_hist + warp * kSelBinsPad;
+  for (int i = r0 + lane; i < r1; i += 32) {
     const uint32_t b = p.fwd_best[qo + i];
     bool keep = b < kInvalidRow;
     const uint32_t d1 = b >> kIdxBits, j = b & kIdxMask;
@@ -84,16 +92,26 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
     }
     const uint32_t bin = p.sort_by_distance ? min(d1, 256u) : 0u;
     s_d[i] = keep ? (uint16_t)bin : (uint16_t)0xFFFFu;
-    if (keep) atomicAdd(&s_hist[bin], 1);
+    if (keep) atomicAdd(&my_hist[bin], 1);
   }
   __syncthreads();
 
-  if (tid < 32) {
-    // ---- exclusive prefix sum over the 257 bins (9 per lane) ----
+  // ---- (2) cursors: within a bin the warps in order, then the bins in order ----
+  for (int b = tid; b < kSelBins; b += nthr) {
+    int run = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const int c = s_hist[w * kSelBinsPad + b];
+      s_hist[w * kSelBinsPad + b] = run;     // exclusive over the warps
+      run += c;
+    }
+    s_tot[b] = run;
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive prefix sum over the 257 bins (9 per lane)
     int local[9], sum = 0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      local[k] = s_hist[lane * 9 + k];   // bins >= 257 are zero padding
+      local[k] = s_tot[lane * 9 + k];   // bins >= 257 are zero padding
       sum += local[k];
     }
     int incl = sum;
@@ -105,30 +123,31 @@ __global__ void __launch_bounds__(1024) select_matches_kernel(const SelectParams
     int run = incl - sum;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      s_hist[lane * 9 + k] = run;        // now: next free output position of this distance
+      s_tot[lane * 9 + k] = run;        // now: first output position of this distance
       run += local[k];
     }
     if (lane == 31) s_count = incl;
-    __syncwarp();
-    // ---- stable placement: ascending query index within a distance ----
-    for (int base = 0; base < nq; base += 32) {
-      const int i = base + lane;
-      const uint32_t dd = i < nq ? (uint32_t)s_d[i] : 0xFFFFu;
-      const bool keep = dd != 0xFFFFu;
-      const uint32_t active = __ballot_sync(0xFFFFFFFFu, keep);
-      if (keep) {
-        const uint32_t grp = __match_any_sync(active, dd);
-        const int leader = __ffs((int)grp) - 1;
-        int pos = 0;
-        if (lane == leader) {
-          pos = s_hist[dd];
-          s_hist[dd] = pos + __popc(grp);
-        }
-        pos = __shfl_sync(grp, pos, leader);
-        s_sorted[pos + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)i;
+  }
+  __syncthreads();
+
+  // ---- (3) stable placement, every warp its own segment and its own cursors ----
+  for (int base = r0; base < r1; base += 32) {
+    const int i = base + lane;
+    const uint32_t dd = i < r1 ? (uint32_t)s_d[i] : 0xFFFFu;
+    const bool keep = dd != 0xFFFFu;
+    const uint32_t active = __ballot_sync(0xFFFFFFFFu, keep);
+    if (keep) {
+      const uint32_t grp = __match_any_sync(active, dd);
+      const int leader = __ffs((int)grp) - 1;
+      int pos = 0;
+      if (lane == leader) {
+        pos = my_hist[dd];
+        my_hist[dd] = pos + __popc(grp);
       }
-      __syncwarp();
+      pos = __shfl_sync(grp, pos, leader);
+      s_sorted[s_tot[dd] + pos + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)i;
     }
+    __syncwarp();
   }
   __syncthreads();
 
@@ -203,8 +222,8 @@ extern "C" int b2s_select_matches(const uint32_t* fwd_best, const uint32_t* fwd_
   int n = 32;
   while (n < max_nq) n <<= 1;
   p.n_sort = n;   // capacity of the shared-memory arrays (rows per pair)
-  const size_t smem = 2 * sizeof(uint16_t) * (size_t)n;
   const int threads = n >= 1024 ? 1024 : (n < 64 ? 64 : n);
+  const size_t smem = 2 * sizeof(uint16_t) * (size_t)n + sizeof(int) * (size_t)(threads / 32) * kSelBinsPad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (smem > 48 * 1024) {
     B2S_CUDA(cudaFuncSetAttribute(select_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -160,3 +160,41 @@ def test_config4_ransac_4096_hypotheses_thousands_of_correspondences():
     assert int(best_h[0]) == ro.select_hypothesis(cd, M)
     assert int(best_c[0]) == int(mask.sum()) == int(cd[int(best_h[0])])
     assert int(best_c[0]) > 0.4 * M
+
+
+def test_config4_selection_10k_rows_equals_oracle():
+    """The selection kernel's per-warp counting sort at BASELINE config #4 size: 10 000 x 10 000 (planted matches,
+    8 % bit noise: hundreds of distance ties), every mode — cross-check only, ratio only, both; sorted by distance
+    (stable: ties keep ascending queryIdx) and unsorted; truncated and complete — against the oracle's selection on
+    the oracle's keys, plus a ragged batch around the segment boundaries of the 32 warps."""
+    from b200slam import _capi
+    from b200slam.frontend import HammingMatcher
+    from oracle import hamming_oracle as ho
+    rng = np.random.default_rng(40)
+    n = 10_000
+    q = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    perm = rng.permutation(n)
+    bits = np.unpackbits(q[perm], axis=1)
+    bits ^= (rng.random(bits.shape) < 0.08).astype(np.uint8)
+    t = np.packbits(bits, axis=1)
+    t[rng.permutation(n)[:3000]] = rng.integers(0, 256, (3000, 32), dtype=np.uint8)      # 30 % of the train rows are strangers
+    m = HammingMatcher(variant=_capi.VARIANT_I8MMA1)
+    (fb, fs, bb), = m.knn2_pairs([q], [t])
+    for use_ratio, use_cross in ((False, True), (True, False), (True, True)):
+        for sort, mm in ((True, None), (True, 500), (False, None), (True, 10_000)):
+            (qi, ti, d), = m.match_pairs([q], [t], use_ratio=use_ratio, use_cross=use_cross, ratio=0.8, sort_by_distance=sort, max_matches=mm)
+            e = ho.select_matches(fb, fs, bb, use_ratio=use_ratio, use_cross=use_cross, ratio=0.8, max_matches=mm, sort_by_distance=sort)
+            np.testing.assert_array_equal(qi, e[0], err_msg=str((use_ratio, use_cross, sort, mm)))
+            np.testing.assert_array_equal(ti, e[1])
+            np.testing.assert_array_equal(d, e[2])
+            assert len(qi) > 400
+    # ragged sizes around the warps' segment boundaries (32 warps x multiples of 32 rows), tie-heavy alphabet
+    sizes = [1, 31, 32, 33, 1023, 1024, 1025, 2047, 2048, 2049, 3000]
+    qs = [rng.integers(0, 4, (a, 32), dtype=np.uint8) for a in sizes]
+    ts = [rng.integers(0, 4, (max(2, a // 2), 32), dtype=np.uint8) for a in sizes]
+    got = m.match_pairs(qs, ts, use_ratio=False, use_cross=True, sort_by_distance=True, max_matches=None)
+    for a, b, (qi, ti, d) in zip(qs, ts, got):
+        e = ho.select_matches(*ho.packed_keys(a, b), use_ratio=False, use_cross=True, ratio=1.0, max_matches=None, sort_by_distance=True)
+        np.testing.assert_array_equal(qi, e[0], err_msg=str(len(a)))
+        np.testing.assert_array_equal(ti, e[1])
+        np.testing.assert_array_equal(d, e[2])

@@ -46,9 +46,9 @@ if a.config == 3:
     print(f"[rank {rank}] captured, collective_in_graph={in_graph}", file=sys.stderr, flush=True)
     for _ in range(2):
         sf.replay()
-    sf.wait()
+    sf.flush()
     torch.cuda.synchronize()
-    u = unpack_records(sf.records().cpu().numpy(), S)
+    u = unpack_records(sf.records()[0].cpu().numpy(), S)
     out = {k: v for k, v in u.items()}
 else:
     rng = np.random.default_rng(9)
