@@ -733,6 +733,8 @@ class RecordView(dict):
         import torch
 
         u = unpack_records(self.records.numpy(), self.stride)
+        if (u["n_matches"] < 0).any():     # the selection kernel's overflow flag (a pair larger than the declared maximum / stride)
+            raise _capi.B2SError("select kernel: a pair did not fit the declared maximum rows / record stride (count = -1)")
         flat = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1))
         dict.update(self, {"count": torch.from_numpy(u["n_matches"].copy()), "best_h": torch.from_numpy(u["best_h"].copy()),
                            "best_count": torch.from_numpy(u["inliers"].copy()), "pair_id": torch.from_numpy(u["pair_id"].copy()),
