@@ -452,14 +452,14 @@ def _capture(env, fn, use_graph=True):
     return g.replay, launches, True
 
 
-def hamming_roofline(env, matcher, batch, n_desc_pairs, steps, peaks=None):
+def hamming_roofline(env, matcher, batch, n_desc_pairs, steps, peaks=None, need_second=True):
     """Kernel-only time of the tensor-core Hamming kernel on `batch` (CUDA events inside the library around that
     one launch; the GPU is kept busy by the call's own pre-pass so no host gap is inside) and its roofline view."""
     import ctypes as C
 
     torch, lib = env.torch, env.lib
     for _ in range(2):
-        matcher.knn2(batch)
+        matcher.knn2(batch, need_second=need_second)
     torch.cuda.synchronize()
     lib.b2s_hamming_kernel_timing(1, None)
     kern, call = [], []
@@ -467,7 +467,7 @@ def hamming_roofline(env, matcher, batch, n_desc_pairs, steps, peaks=None):
         env.flush.fill_(0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        matcher.knn2(batch)
+        matcher.knn2(batch, need_second=need_second)
         e1.record()
         torch.cuda.synchronize()
         v = C.c_float(0.0)
@@ -479,7 +479,7 @@ def hamming_roofline(env, matcher, batch, n_desc_pairs, steps, peaks=None):
     lib.b2s_hamming_last_plan(*[C.byref(x) for x in plan])
     t_k, t_call = float(np.mean(kern)) * 1e-3, float(np.mean(call)) * 1e-3
     ops = 2.0 * 256.0 * n_desc_pairs
-    out = {"kernel_ms": t_k * 1e3, "call_ms": t_call * 1e3, "achieved_top_s": ops / t_k / 1e12, "int8_ops": ops,
+    out = {"kernel_ms": t_k * 1e3, "call_ms": t_call * 1e3, "achieved_top_s": ops / t_k / 1e12, "int8_ops": ops, "second_neighbour": bool(need_second),
            "plan": {"query_subtiles_per_item": plan[0].value, "train_split": plan[1].value, "ctas": plan[2].value}}
     if peaks:
         out["frac_of_int8_peak"] = ops / t_k / peaks["i8"]
@@ -593,7 +593,7 @@ def _roof_from(hr, peaks, kernel, traffic=None, traffic_src=None, extra=None):
     roof = {"bound": "tensor", "achieved": hr["achieved_top_s"], "peak": peaks["i8"] / 1e12, "unit": "TOP/s (int8)",
             "frac": hr["frac_of_int8_peak"], "traffic": traffic, "kernel": kernel, "kernel_ms": hr["kernel_ms"],
             "algorithmic_int8_ops_per_launch": hr["int8_ops"], "frac_of_2x_measured_bf16": hr["frac_of_2x_measured_bf16"],
-            "plan": hr["plan"],
+            "plan": hr["plan"], "second_neighbour_computed": hr["second_neighbour"],
             "stage": {"what": "whole Hamming call: 3 memsets + operand expansion + the kernel (+ the merge of a train-axis split)",
                       "ms": hr["call_ms"], "frac": hr["int8_ops"] / (hr["call_ms"] * 1e-3) / peaks["i8"]},
             "peak_source": "b2s_mma_microbench measured in this run (dense tcgen05.mma kind::i8 M128.N128.K32 from shared memory); MEASURED_PEAKS.json "
@@ -647,6 +647,7 @@ def run_config2(env, a):
     value = pairs_per_step * a.steps / (total_ms * 1e-3)
 
     # ---- sustained behaviour: the step replayed back to back for >= 2 s (clocks / power sampled over it) ----
+    import dataclasses
     soak = None
     if world == 1 or rank == 0:
         n_soak = max(10, int(2.2e3 / max(total_ms / a.steps, 1e-3)))
@@ -671,8 +672,16 @@ def run_config2(env, a):
                 "sm_mhz": sc["sm_mhz"], "power_w_max": sc["power_w_max"], "reasons": sc["reasons"], "clock_samples": sc["samples"],
                 "note": "the timed step replayed back to back without L2 flushes; sustained clocks and power next to the 20-step figure"}
 
+    # ---- the same step with the reference's DEFAULT matcher (cross_check=True, no ratio test: feature_pipeline.py.bak:17,81-82,
+    #      configs/pipeline/kitti_default.json): the Hamming kernel then skips the second neighbour ----
+    sfc = ShardedFrontend(dataclasses.replace(cfg, use_ratio=False), world * P, variant=env.variant, sets_per_gather=a.sub_batches)
+    step_c, _, _ = sharded_step(env, sfc, batch_list, use_graph=not a.no_graph)
+    ms_c = env.timed(step_c, max(3, a.steps // 2), 2)
+    sfc.flush()
+    value_cc = pairs_per_step * len(ms_c) / (env.max_over_ranks(float(np.sum(ms_c))) * 1e-3)
+    del sfc
+
     # ---- the same step, additionally refitting E on the inliers and recovering (R, t) (K7) into the records ----
-    import dataclasses
     sfp = ShardedFrontend(dataclasses.replace(cfg, with_pose=True), world * P, variant=env.variant, sets_per_gather=a.sub_batches)
 
     step_p, _, _ = sharded_step(env, sfp, batch_list, use_graph=not a.no_graph)
@@ -793,6 +802,9 @@ def run_config2(env, a):
                                        "largest complete count are scored to the end; reported beside, not instead of, `value` (all %d hypotheses scored)"
                                        % (same_winner, a.hyps),
              "winner_only_identical": same_winner, "gpu_launches_per_step_winner_only": launches_w,
+             "value_cross_check_matcher": value_cc,
+             "value_cross_check_matcher_note": "same step with the reference's default matcher (cross_check=True, no ratio test): the tensor-core kernel "
+                                               "skips the per-row second neighbour (B2S_HAMMING_BEST_ONLY), which BFMatcher(crossCheck=True).match never reads",
              "value_with_pose": value_pose,
              "value_with_pose_note": "same step + n-point refit of E on the winner's inliers + decomposition / cheirality vote (K7), R | t in the records; "
                                      "outside the metric's unit (SURVEY 8d), reported beside it",
@@ -1036,7 +1048,8 @@ def run_config5(env, a, peaks=None, brief=False):
     if peaks is None and rank == 0:
         peaks = measured_peaks(env)
     m = sw.sweep
-    hr = hamming_roofline(env, m.matcher, m._batch(N), float(hi - lo) * N * N, a.steps, peaks)
+    hr = hamming_roofline(env, m.matcher, m._batch(N), float(hi - lo) * N * N, a.steps, peaks, need_second=False)   # the sweep's kernel: cross-check only
+    hr_full = hamming_roofline(env, m.matcher, m._batch(N), float(hi - lo) * N * N, max(3, a.steps // 2), peaks)
 
     # e2e: the query frame arrives from pinned host memory (80 KB), the gathered candidate records + per-keyframe counts go back
     out_host = torch.empty(sw.gather.buf.shape, dtype=torch.uint8).pin_memory()
@@ -1057,7 +1070,8 @@ def run_config5(env, a, peaks=None, brief=False):
     check = {"top_frame_ids": cand["pair_id"].tolist(), "top_match_counts": cand["n_matches"].tolist(), "top_inliers": cand["inliers"].tolist(),
              "planted_keyframe": best, "planted_found_first": bool(len(cand["pair_id"]) and int(cand["pair_id"][0]) == best),
              "mean_matches_per_keyframe": float(np.mean(counts))}
-    roof = _roof_from(hr, peaks, "hamming_knn2_i8s_kernel")
+    roof = _roof_from(hr, peaks, "hamming_knn2_i8s_kernel<1, false, 2, false> (best neighbour only: BFMatcher(crossCheck=True).match never reads the second)",
+                      extra={"with_second_neighbour": {k: hr_full[k] for k in ("kernel_ms", "achieved_top_s", "frac_of_int8_peak")}})
     e2e = {"value": n_kf * len(e2e_ms) / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(N * 40), "d2h_bytes_per_step": int(out_host.numel()),
            "api": "b200slam.sharding.ShardedSweep.query / result_host", "ms_per_step": e2e_total / len(e2e_ms)}
     return _base_line(env, a, value, total_ms, "strong", clk, roof, e2e, {}, launches,

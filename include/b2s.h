@@ -45,6 +45,11 @@ extern "C" {
 #define B2S_VARIANT_POPC 0  /* LOP3/POPC integer-pipe kernel (K1) */
 #define B2S_VARIANT_I8MMA 1 /* tcgen05.mma kind::i8 +-8 contraction, two products D and D^T (K2) */
 #define B2S_VARIANT_I8MMA1 2 /* same contraction, ONE product; column minima by warp butterfly (K2s) */
+/* OR-ed into `variant` (K2s only; the other kernels ignore it): the per-row SECOND neighbour is not needed —
+ * fwd_second is left "none".  That is BFMatcher(crossCheck=True).match (feature_pipeline.py.bak:82,
+ * persistent_map.py:266, keyframe_manager.py:126,141), the reference's default matcher; only knnMatch + ratio
+ * (.bak:84-91) and match_orb_descriptors (homography.py:9-26) read the second neighbour. */
+#define B2S_HAMMING_BEST_ONLY 0x100
 
 int b2s_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py gpu_launches). */
@@ -210,7 +215,7 @@ int b2s_five_point_batched(const float* corr, const int32_t* c_off, const int32_
  * tiles start at tile blk_tile0[b] (prefix sum of ceil(rows / 128); total_tiles in all);
  * q_xtile[p] / t_xtile[p] = first tile of pair p's query / train block; q_off / t_off = CSR of the
  * OUTPUT rows (q_off[p+1] - q_off[p] must equal the query block's rows).  All index arrays int32 on
- * the device.  Outputs and t_split as b2s_hamming_knn2_batched.  workspace: b2s_hamming_shared_workspace_bytes
+ * the device.  Outputs and t_split as b2s_hamming_knn2_batched; need_second = 0 is B2S_HAMMING_BEST_ONLY.  workspace: b2s_hamming_shared_workspace_bytes
  * (same n_pairs / total_nq / max_nq / max_nt / t_split as the call). */
 size_t b2s_hamming_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt,
                                           int t_split);
@@ -218,7 +223,7 @@ int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const 
                             const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                             const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                             int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, int need_second, void* workspace,
                             size_t workspace_bytes, void* stream);
 /* Diagnostics: work decomposition of the most recent single-product launch — query sub-tiles per
  * work item (2 or 4), train-axis split, CTAs. */

@@ -153,7 +153,7 @@ def cross_check_batch(query: np.ndarray, blocks: Sequence[np.ndarray], query_is_
         b = PairBatch.from_host([query] * n, blocks)
         b.q_desc = torch.from_numpy(np.ascontiguousarray(query, dtype=np.uint8)).cuda()
         b.q_src = torch.zeros(n, dtype=torch.int32, device="cuda")
-    keys = m.knn2(b)
+    keys = m.knn2(b, need_second=False)
     sel = m.select(b, keys, use_ratio=False, use_cross=True, sort_by_distance=False, max_matches=None)
     packed = torch.stack([sel.out_q, sel.out_t, sel.out_d]).cpu().numpy()
     cnt = sel.count.cpu().numpy()
@@ -336,7 +336,7 @@ class BatchedMapRelocalizer:
                           q_off_host=q_off, t_off_host=off, q_src=torch.full((n,), int(off[-1]), dtype=torch.int32, device="cuda"),
                           t_src=off_d[:n].contiguous(), shared=shared)
         m = _matcher()
-        keys = m.knn2(batch)
+        keys = m.knn2(batch, need_second=False)
         sel = m.select(batch, keys, use_ratio=False, use_cross=True, sort_by_distance=False, max_matches=None)
         counts = sel.count.cpu().numpy().astype(np.int64)
         ids = np.array([int(kf.frame_id) for kf in kfs])

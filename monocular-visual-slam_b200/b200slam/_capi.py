@@ -25,6 +25,7 @@ ABI_VERSION = 2
 VARIANT_POPC = 0
 VARIANT_I8MMA = 1
 VARIANT_I8MMA1 = 2
+HAMMING_BEST_ONLY = 0x100      # OR-ed into the variant: fwd_second not needed (cross-check-only matching)
 
 PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "imad": 6, "redux": 7, "shfl": 8,
             "vmin_u16x2": 9, "vmin3_u16x2": 10, "viaddmax_u16x2": 11, "setp_sel": 12, "prmt": 13, "ffma2": 14, "ffma2+ffma": 15, "ffma2+2ffma": 16}
@@ -63,7 +64,7 @@ def _declare(lib):
     lib.b2s_hamming_last_plan.restype = None
     lib.b2s_hamming_last_plan.argtypes = [ip, ip, ip]
     lib.b2s_hamming_knn2_shared.restype = i32
-    lib.b2s_hamming_knn2_shared.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, sz, vp]
+    lib.b2s_hamming_knn2_shared.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, sz, vp]
     lib.b2s_hamming_set_config.restype = i32
     lib.b2s_hamming_set_config.argtypes = [i32, i32, i32]
     lib.b2s_hamming_get_config.restype = i32

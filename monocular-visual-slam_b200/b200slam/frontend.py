@@ -200,7 +200,9 @@ class HammingMatcher:
         self._ws = None
         self._coff = {}
 
-    def knn2(self, b: PairBatch) -> Keys:
+    def knn2(self, b: PairBatch, need_second: bool = True) -> Keys:
+        """need_second=False (cross-check-only matching, the reference's default matcher): the tensor-core kernel
+        skips the per-row second neighbour — fwd_second is all "none" — and runs ~15 % faster."""
         torch = _capi.require_cuda()
         dev = b.q_desc.device
         nq, nt = b.total_nq, b.total_nt
@@ -217,7 +219,7 @@ class HammingMatcher:
             check(self._lib.b2s_hamming_knn2_shared(
                 ptr(b.q_desc), ptr(sh.row0), ptr(sh.rows), ptr(sh.tile0), sh.n_blocks, sh.total_tiles, sh.max_rows,
                 ptr(sh.q_xtile), ptr(sh.t_xtile), ptr(b.q_off), ptr(b.t_off), b.n_pairs, nq, nt, b.max_nq, b.max_nt,
-                ptr(fb), ptr(fs), ptr(bb), self.t_split, self._ws.data_ptr(), ws_bytes, current_stream()))
+                ptr(fb), ptr(fs), ptr(bb), self.t_split, int(need_second), self._ws.data_ptr(), ws_bytes, current_stream()))
             return Keys(fb[:nq], fs[:nq], bb[:nt])
         if nq > 0 and (self.variant != _capi.VARIANT_POPC or self.t_split != 1):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -233,7 +235,7 @@ class HammingMatcher:
         check(self._lib.b2s_hamming_knn2_batched(
             ptr(b.q_desc), ptr(b.t_desc), ptr(b.q_off), ptr(b.t_off), ptr(b.q_src), ptr(b.t_src),
             b.n_pairs, nq, nt, b.max_nq, b.max_nt, ptr(fb), ptr(fs), ptr(bb),
-            self.variant, self.t_split, ws_ptr, ws_bytes, current_stream()))
+            self.variant | (0 if need_second else _capi.HAMMING_BEST_ONLY), self.t_split, ws_ptr, ws_bytes, current_stream()))
         return Keys(fb[:nq], fs[:nq], bb[:nt])
 
     def select(self, b: PairBatch, k: Keys, *, use_ratio: bool, use_cross: bool, ratio: float = 0.8,
@@ -281,7 +283,7 @@ class HammingMatcher:
             return []
         if b.max_nq > _capi.SELECT_MAX_QUERIES:
             raise ValueError(f"more than {_capi.SELECT_MAX_QUERIES} query descriptors in one pair")
-        keys = self.knn2(b)
+        keys = self.knn2(b, need_second=bool(use_ratio))
         sel = self.select(b, keys, use_ratio=use_ratio, use_cross=use_cross, ratio=ratio,
                           sort_by_distance=sort_by_distance, max_matches=max_matches)
         packed = torch.stack([sel.out_q, sel.out_t, sel.out_d]).cpu().numpy()
@@ -691,7 +693,7 @@ class Frontend:
         before the record kernel — where ShardedFrontend starts and joins the collective of the PREVIOUS batch, so
         that it overlaps the multi-wave RANSAC kernels and never the persistent one-CTA-per-SM Hamming kernel."""
         c = self.cfg
-        keys = self.matcher.knn2(b)
+        keys = self.matcher.knn2(b, need_second=bool(c.use_ratio))
         sel = self.matcher.select(b, keys, use_ratio=c.use_ratio, use_cross=c.use_cross, ratio=c.ratio,
                                   sort_by_distance=True, max_matches=c.max_matches, with_corr=True,
                                   compact=True)
@@ -1173,7 +1175,7 @@ class MapSweep:
         torch = _capi.require_cuda()
         c, S, k = self.cfg, self.cfg.max_matches, min(self.top, max(self.n_kf, 1))
         b = self._batch(self.nq)
-        keys = self.matcher.knn2(b)
+        keys = self.matcher.knn2(b, need_second=False)          # cross-check only (persistent_map.py:266): no second neighbour
         sel = self.matcher.select(b, keys, use_ratio=False, use_cross=True, sort_by_distance=True, max_matches=S,
                                   with_corr=True, compact=True, with_total=True)
         top_idx, c_off, c_cnt, top_id = rank_pairs(sel.total, k, ids=self.frame_ids, sel_count=sel.count, stride=S, with_ids=True)

@@ -44,14 +44,14 @@ size_t hamming_i8_workspace_bytes(int n_pairs, int total_nq, int max_nq, int max
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, int t_split,
-                      void* workspace, size_t workspace_bytes, int single, cudaStream_t st);
+                      void* workspace, size_t workspace_bytes, int single, int need_second, cudaStream_t st);
 
 size_t hamming_i8_shared_workspace_bytes(int total_tiles, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split);
 int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const int32_t* blk_rows,
                              const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                              const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                              int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, int need_second, void* workspace,
                              size_t workspace_bytes, cudaStream_t st);
 void hamming_i8_last_plan(int* subs, int* t_split, int* grid);
 
@@ -162,15 +162,17 @@ int b2s_hamming_knn2_batched(const uint8_t* q_desc, const uint8_t* t_desc, const
   B2S_REQUIRE((total_nq == 0 || q_desc) && (total_nt == 0 || t_desc), "null descriptor pointer");
   B2S_REQUIRE((((uintptr_t)q_desc | (uintptr_t)t_desc) & 15u) == 0, "descriptor buffers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == B2S_VARIANT_POPC) {
+  if ((variant & ~B2S_HAMMING_BEST_ONLY) == B2S_VARIANT_POPC) {
     return hamming_popc_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt,
                                max_nq, max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
                                st);
   }
+  const int need_second = !(variant & B2S_HAMMING_BEST_ONLY);
+  variant &= ~B2S_HAMMING_BEST_ONLY;
   if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1) {
     return hamming_i8_launch(q_desc, t_desc, q_off, t_off, q_src_row, t_src_row, n_pairs, total_nq, total_nt, max_nq,
                              max_nt, fwd_best, fwd_second, bwd_best, t_split, workspace, workspace_bytes,
-                             variant == B2S_VARIANT_I8MMA1, st);
+                             variant == B2S_VARIANT_I8MMA1, need_second, st);
   }
   set_error("Hamming variant %d is not built into this library", variant);
   return B2S_ERR_UNSUPPORTED;
@@ -186,7 +188,7 @@ int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const 
                             const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                             const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                             int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                            uint32_t* fwd_second, uint32_t* bwd_best, int t_split, int need_second, void* workspace,
                             size_t workspace_bytes, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(n_pairs >= 0 && n_blocks >= 0 && total_tiles >= 0 && total_nq >= 0 && total_nt >= 0 && max_nq >= 0 &&
@@ -200,11 +202,12 @@ int b2s_hamming_knn2_shared(const uint8_t* desc, const int32_t* blk_row0, const 
   B2S_REQUIRE(((uintptr_t)desc & 15u) == 0, "descriptor buffer must be 16-byte aligned");
   return hamming_i8_shared_launch(desc, blk_row0, blk_rows, blk_tile0, n_blocks, total_tiles, max_block_rows, q_xtile,
                                   t_xtile, q_off, t_off, n_pairs, total_nq, total_nt, max_nq, max_nt, fwd_best,
-                                  fwd_second, bwd_best, t_split, workspace, workspace_bytes,
+                                  fwd_second, bwd_best, t_split, need_second, workspace, workspace_bytes,
                                   static_cast<cudaStream_t>(stream));
 }
 
 size_t b2s_hamming_workspace_bytes_v(int variant, int n_pairs, int total_nq, int max_nq, int max_nt, int t_split) {
+  variant &= ~B2S_HAMMING_BEST_ONLY;
   if (variant == B2S_VARIANT_I8MMA || variant == B2S_VARIANT_I8MMA1)
     return b2s::hamming_i8_workspace_bytes(n_pairs, total_nq, max_nq, max_nt, variant == B2S_VARIANT_I8MMA1 ? t_split : 1);
   return b2s_hamming_workspace_bytes(total_nq, t_split);

@@ -666,9 +666,15 @@ template <int SUBS> struct I8sCfg {
                                   16 * 32 * sizeof(uint4);
 };
 
-template <int EPI, bool DBG, int SUBS>
+// TOP2 = false: the per-row SECOND neighbour is not computed (fwd_second stays "none").  The reference's production
+// matcher — BFMatcher(crossCheck=True).match at feature_pipeline.py.bak:82 (cross_check is the default and what
+// configs/pipeline/kitti_default.json sets), persistent_map.py:266, keyframe_manager.py:126,141 — never looks at it;
+// only the kNN + ratio mode (.bak:84-91) and match_orb_descriptors do.  Dropping the second pass removes 64 of the
+// epilogue's ~164 packed min/max instructions per thread and tile pair, and the epilogue's ALU pipe is the kernel's limiter.
+template <int EPI, bool DBG, int SUBS, bool TOP2 = true>
 __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const I8Params p) {
   static_assert(SUBS == 2 || (SUBS == 4 && EPI == 1), "4 sub-tiles per item: 16x256b epilogue only");
+  static_assert(TOP2 || EPI == 1, "best-only: 16x256b epilogue only");
   constexpr int kStages = I8sCfg<SUBS>::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_q = smem;                                   // SUBS x 36 KB: the item's query sub-tiles (18 chunks each)
@@ -1035,39 +1041,49 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
               m1 = __vimax3_u16x2(m1, B2S_R1(r, i), B2S_R1(r, i + 1));
             }
             const uint32_t bb0 = __vmaxu2(m0, B2S_R0(r, 15)), bb1 = __vmaxu2(m1, B2S_R1(r, 15));
-            // pass 2: values are unique within a row (or zero padding, never the largest of a real row), so
-            // x - best wraps to 0 exactly for the maximum itself and keeps the order of everything below it
-            const uint32_t cn0 = __vneg2(bb0), cn1 = __vneg2(bb1);
-            uint32_t a00 = 0u, a01 = 0u, a10 = 0u, a11 = 0u;
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              a00 = __viaddmax_u16x2(B2S_R0(r, i), cn0, a00);
-              a10 = __viaddmax_u16x2(B2S_R1(r, i), cn1, a10);
-              a01 = __viaddmax_u16x2(B2S_R0(r, i + 1), cn0, a01);
-              a11 = __viaddmax_u16x2(B2S_R1(r, i + 1), cn1, a11);
-            }
-            const uint32_t ss0 = __vadd2(__vmaxu2(a00, a01), bb0);  // second largest per 16-bit lane (mod 2^16 per lane)
-            const uint32_t ss1 = __vadd2(__vmaxu2(a10, a11), bb1);
             // fold the even / odd halves of both rows at once: x = (row a even | row b even), y = (.. odd | .. odd)
             const uint32_t x = __byte_perm(bb0, bb1, 0x5410), y = __byte_perm(bb0, bb1, 0x7632);
-            const uint32_t sx = __byte_perm(ss0, ss1, 0x5410), sy = __byte_perm(ss0, ss1, 0x7632);
             pb[h] = __vmaxu2(x, y);
-            ps[h] = __vimax3_u16x2(__vminu2(x, y), sx, sy);
+            if constexpr (TOP2) {
+              // pass 2: values are unique within a row (or zero padding, never the largest of a real row), so
+              // x - best wraps to 0 exactly for the maximum itself and keeps the order of everything below it
+              const uint32_t cn0 = __vneg2(bb0), cn1 = __vneg2(bb1);
+              uint32_t a00 = 0u, a01 = 0u, a10 = 0u, a11 = 0u;
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                a00 = __viaddmax_u16x2(B2S_R0(r, i), cn0, a00);
+                a10 = __viaddmax_u16x2(B2S_R1(r, i), cn1, a10);
+                a01 = __viaddmax_u16x2(B2S_R0(r, i + 1), cn0, a01);
+                a11 = __viaddmax_u16x2(B2S_R1(r, i + 1), cn1, a11);
+              }
+              const uint32_t ss0 = __vadd2(__vmaxu2(a00, a01), bb0);  // second largest per 16-bit lane (mod 2^16 per lane)
+              const uint32_t ss1 = __vadd2(__vmaxu2(a10, a11), bb1);
+              const uint32_t sx = __byte_perm(ss0, ss1, 0x5410), sy = __byte_perm(ss0, ss1, 0x7632);
+              ps[h] = __vimax3_u16x2(__vminu2(x, y), sx, sy);
+            }
           }
           // the four lanes that share these rows hold disjoint columns: merge best / second, both row pairs
 #pragma unroll
           for (int o = 1; o <= 2; o <<= 1) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, pb[h], o), os = __shfl_xor_sync(0xFFFFFFFFu, ps[h], o);
-              ps[h] = __vimax3_u16x2(__vminu2(pb[h], ob), ps[h], os);
+              const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, pb[h], o);
+              if constexpr (TOP2) {
+                const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, ps[h], o);
+                ps[h] = __vimax3_u16x2(__vminu2(pb[h], ob), ps[h], os);
+              }
               pb[h] = __vmaxu2(pb[h], ob);
             }
           }
           // lane%4 = k finishes row k: complement (acc = ~key), then the keys carry + row: take it off before widening
-          const uint32_t best16 = ~__byte_perm(pb[0], pb[1], pick) & 0xFFFFu, sec16 = ~__byte_perm(ps[0], ps[1], pick) & 0xFFFFu;
-          top2_insert(gbest, gsecond, key16_to_key32(best16 - (uint32_t)row, (uint32_t)tbase));
-          top2_insert(gbest, gsecond, key16_to_key32(sec16 - (uint32_t)row, (uint32_t)tbase));
+          const uint32_t best16 = ~__byte_perm(pb[0], pb[1], pick) & 0xFFFFu;
+          if constexpr (TOP2) {
+            const uint32_t sec16 = ~__byte_perm(ps[0], ps[1], pick) & 0xFFFFu;
+            top2_insert(gbest, gsecond, key16_to_key32(best16 - (uint32_t)row, (uint32_t)tbase));
+            top2_insert(gbest, gsecond, key16_to_key32(sec16 - (uint32_t)row, (uint32_t)tbase));
+          } else {
+            gbest = min(gbest, key16_to_key32(best16 - (uint32_t)row, (uint32_t)tbase));
+          }
         }
         // ---- column minima: the 4 rows inside the thread, then 3 butterfly levels over lane bits 2..4 ----
         uint32_t y[64];   // colmin_step's signature; only y[0..15] are live
@@ -1132,7 +1148,8 @@ __global__ void __launch_bounds__(kI8sThreads, 1) hamming_knn2_i8s_kernel(const 
       }
       if (writer) {
         const int qo = p.q_off[pair];
-        const uint32_t ob = gbest >= kKey32Pad ? kNone : gbest, os = gsecond >= kKey32Pad ? kNone : gsecond;
+        // best-only: gsecond is not a second neighbour (the merge of the two sets above put the larger of their bests there)
+        const uint32_t ob = gbest >= kKey32Pad ? kNone : gbest, os = (!TOP2 || gsecond >= kKey32Pad) ? kNone : gsecond;
         if (t_split > 1) {
           p.partial[(size_t)part * p.total_nq + qo + q0 + row] = make_uint2(ob, os);
         } else {
@@ -1382,13 +1399,13 @@ static int clear_keys(uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_be
 
 // the single-product kernel: picks the instantiation, opts into its shared memory (per launch: the
 // attribute is per device, and a process may drive several), brackets it with the timing events
-template <int EPI, bool DBG, int SUBS>
+template <int EPI, bool DBG, int SUBS, bool TOP2 = true>
 static int launch_i8s_inst(const I8Params& p, int grid, cudaStream_t st) {
   static bool attr_set[64] = {false};   // one flag array per instantiation
   if (first_use_on_device(attr_set))
-    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<EPI, DBG, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8s_kernel<EPI, DBG, SUBS, TOP2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)I8sCfg<SUBS>::kSmem));
-  hamming_knn2_i8s_kernel<EPI, DBG, SUBS><<<grid, kI8sThreads, I8sCfg<SUBS>::kSmem, st>>>(p);
+  hamming_knn2_i8s_kernel<EPI, DBG, SUBS, TOP2><<<grid, kI8sThreads, I8sCfg<SUBS>::kSmem, st>>>(p);
   return B2S_OK;
 }
 static int g_i8_last_plan[3] = {0, 0, 0};   // subs, t_split, grid of the most recent launch (diagnostics)
@@ -1397,7 +1414,7 @@ void hamming_i8_last_plan(int* subs, int* t_split, int* grid) {
   if (t_split) *t_split = g_i8_last_plan[1];
   if (grid) *grid = g_i8_last_plan[2];
 }
-static int launch_i8s(I8Params& p, const I8sPlan& pl, int total_nq, uint8_t* partial_ws, cudaStream_t st) {
+static int launch_i8s(I8Params& p, const I8sPlan& pl, int total_nq, uint8_t* partial_ws, bool need_second, cudaStream_t st) {
   p.t_split = pl.t_split;
   p.total_nq = total_nq;
   p.partial = pl.t_split > 1 ? reinterpret_cast<uint2*>(partial_ws) : nullptr;
@@ -1409,20 +1426,25 @@ static int launch_i8s(I8Params& p, const I8sPlan& pl, int total_nq, uint8_t* par
   if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[0], st));
   int rc;
   if (p.mode & 16) rc = launch_i8s_inst<0, true, 2>(p, grid, st);            // 32x32b epilogue (A/B partner)
+  else if (!need_second && pl.subs == 2 && !p.dbg) rc = launch_i8s_inst<1, false, 2, false>(p, grid, st);   // best neighbour only
   else if (pl.subs == 4) rc = p.dbg ? launch_i8s_inst<1, true, 4>(p, grid, st) : launch_i8s_inst<1, false, 4>(p, grid, st);
   else rc = p.dbg ? launch_i8s_inst<1, true, 2>(p, grid, st) : launch_i8s_inst<1, false, 2>(p, grid, st);
   if (rc) return rc;
   B2S_CUDA(cudaGetLastError());
   if (g_i8_timing) B2S_CUDA(cudaEventRecord(g_i8_ev[1], st));
   note_launch();
-  if (pl.t_split > 1) return hamming_merge_launch(p.partial, total_nq, pl.t_split, p.fwd_best, p.fwd_second, st);
+  if (pl.t_split > 1) {
+    if (int rc2 = hamming_merge_launch(p.partial, total_nq, pl.t_split, p.fwd_best, p.fwd_second, st)) return rc2;
+    // best-only: the merge folded the parts' BEST keys into fwd_second; that is not a second neighbour
+    if (!need_second) B2S_CUDA(cudaMemsetAsync(p.fwd_second, 0xFF, sizeof(uint32_t) * (size_t)total_nq, st));
+  }
   return B2S_OK;
 }
 
 int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, const int32_t* t_off,
                       const int32_t* q_src, const int32_t* t_src, int n_pairs, int total_nq, int total_nt, int max_nq,
                       int max_nt, uint32_t* fwd_best, uint32_t* fwd_second, uint32_t* bwd_best, int t_split,
-                      void* workspace, size_t workspace_bytes, int single, cudaStream_t st) {
+                      void* workspace, size_t workspace_bytes, int single, int need_second, cudaStream_t st) {
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;  // rows of pairs without train descriptors keep "none"
   if (total_nq == 0 || total_nt == 0 || max_nq == 0 || max_nt == 0) return B2S_OK;
@@ -1463,7 +1485,7 @@ int hamming_i8_launch(const uint8_t* q, const uint8_t* t, const int32_t* q_off, 
   p.t_split = 1;
   p.total_nq = total_nq;
   p.partial = nullptr;
-  if (single) return launch_i8s(p, pl, total_nq, static_cast<uint8_t*>(workspace) + tiles_bytes, st);
+  if (single) return launch_i8s(p, pl, total_nq, static_cast<uint8_t*>(workspace) + tiles_bytes, need_second != 0, st);
   static bool attr_set[64] = {false};
   if (first_use_on_device(attr_set))
     B2S_CUDA(cudaFuncSetAttribute(hamming_knn2_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8SmemBytes));
@@ -1488,7 +1510,7 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
                              const int32_t* blk_tile0, int n_blocks, int total_tiles, int max_block_rows,
                              const int32_t* q_xtile, const int32_t* t_xtile, const int32_t* q_off, const int32_t* t_off,
                              int n_pairs, int total_nq, int total_nt, int max_nq, int max_nt, uint32_t* fwd_best,
-                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, void* workspace,
+                             uint32_t* fwd_second, uint32_t* bwd_best, int t_split, int need_second, void* workspace,
                              size_t workspace_bytes, cudaStream_t st) {
   B2S_REQUIRE(n_blocks <= 65535, "n_blocks %d exceeds grid.y limit 65535; split the batch", n_blocks);
   if (int rc = clear_keys(fwd_best, fwd_second, bwd_best, total_nq, total_nt, st)) return rc;
@@ -1522,7 +1544,7 @@ int hamming_i8_shared_launch(const uint8_t* desc, const int32_t* blk_row0, const
   p.t_xt = t_xtile;
   p.dbg = g_i8_dbg;
   p.mode = g_i8_mode & ~16;
-  return launch_i8s(p, pl, total_nq, x + tiles_bytes, st);
+  return launch_i8s(p, pl, total_nq, x + tiles_bytes, need_second != 0, st);
 }
 
 }  // namespace b2s

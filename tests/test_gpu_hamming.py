@@ -353,3 +353,32 @@ def test_k2s_shared_blocks_with_split(force, t_split):
     popc = HammingMatcher(variant=_capi.VARIANT_POPC).knn2(b)
     for name in ("fwd_best", "fwd_second", "bwd_best"):
         assert np.array_equal(getattr(got, name).cpu().numpy(), getattr(popc, name).cpu().numpy()), name
+
+
+@pytest.mark.parametrize("t_split", [0, 3])
+def test_k2s_best_only_variant(hg, t_split):
+    """B2S_HAMMING_BEST_ONLY (cross-check-only matching: BFMatcher(crossCheck=True).match never reads the second
+    neighbour): fwd_best and bwd_best are those of the full kernel / the oracle, fwd_second is all "none", and the
+    cross-check front door returns cv2's matches — per-pair and shared-block entries, with and without a train split."""
+    import torch
+    from b200slam import _capi
+    from b200slam.frontend import HammingMatcher, PairBatch, sequence_batch
+    names = list(hg["names"])
+    qs, ts = [_pad(hg[f"{n}/q"]) for n in names], [_pad(hg[f"{n}/t"]) for n in names]
+    m = HammingMatcher(variant=_capi.VARIANT_I8MMA1, t_split=t_split)
+    b = PairBatch.from_host(qs, ts)
+    full, best = m.knn2(b), m.knn2(b, need_second=False)
+    assert torch.equal(full.fwd_best, best.fwd_best) and torch.equal(full.bwd_best, best.bwd_best)
+    assert bool((best.fwd_second == -1).all())                       # 0xFFFFFFFF = "none"
+    out = m.match_pairs([hg[f"{n}/q"] for n in names], [hg[f"{n}/t"] for n in names], use_ratio=False, use_cross=True, sort_by_distance=False)
+    for n, (qi, ti, d) in zip(names, out):
+        np.testing.assert_array_equal(qi, hg[f"{n}/cc_q"], err_msg=n)
+        np.testing.assert_array_equal(ti, hg[f"{n}/cc_t"], err_msg=n)
+        np.testing.assert_array_equal(d, hg[f"{n}/cc_d"], err_msg=n)
+    rng = np.random.default_rng(79)
+    N, counts = 700, np.array([700, 1, 128, 0, 513, 129, 640], np.int32)
+    desc = torch.from_numpy(rng.integers(0, 4, (len(counts) * N, 32), dtype=np.uint8)).cuda()
+    sb = sequence_batch(desc, torch.zeros((len(counts) * N, 2), dtype=torch.float32, device="cuda"), counts, 0, len(counts) - 1, N)
+    full, best = m.knn2(sb), m.knn2(sb, need_second=False)
+    assert torch.equal(full.fwd_best, best.fwd_best) and torch.equal(full.bwd_best, best.bwd_best)
+    assert bool((best.fwd_second == -1).all())
