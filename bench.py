@@ -132,13 +132,18 @@ def cpu_arm(a, n_pairs, steps=1, warmup=0):
     kw = dict(max_iter=a.hyps, max_matches=mm)
     if a.config == 5:      # the sweep's unit: cross-check match of the query against ONE keyframe; only the top 5 of 4541 are verified
         kw.update(ratio=None, ransac=False)
-    for _ in range(warmup):
-        rp.run_pairs(pairs[: max(1, min(len(pairs), cores))], workers=cores, **kw)
-    times, res = [], None
-    for _ in range(steps):
-        res, sec, workers = rp.run_pairs(pairs, workers=cores, **kw)
-        times.append(sec)
-    sec = float(np.mean(times))
+    times, res, sec_full = [], None, None
+    with rp.PairPool(cores) as pool:                                         # ONE pool, every worker initialised before the clock
+        workers = pool.workers
+        for _ in range(warmup):
+            pool.run(pairs[: max(1, min(len(pairs), cores))], **kw)
+        for _ in range(steps):
+            res, sec = pool.run(pairs, **kw)
+            times.append(sec)
+        if a.config in (2, 3):   # same work as the GPU unit (every hypothesis scored) on a smaller sample
+            nfull = max(1, min(len(pairs), cores))
+            _, sec_full = pool.run(pairs[:nfull], full_budget=True, **kw)
+    sec = float(np.median(times))
     out = {"value": n_pairs / sec, "unit": UNIT, "cores": workers, "kind": rp.kind(), "cpu_model": rp.cpu_model(),
            "sample": f"{n_pairs} pairs/step x {steps} step(s), mode (ii) of SURVEY 8d: one process per core, each ONE OpenCV thread and ONE BLAS thread; "
                      f"per pair cv2.BFMatcher knnMatch + ratio and crossCheck match, sort, top-{mm}, then the reference's Python RANSAC loop with its "
@@ -150,10 +155,8 @@ def cpu_arm(a, n_pairs, steps=1, warmup=0):
         out["sample"] = (f"{n_pairs} (keyframe, query) pairs, one process per core (ONE OpenCV thread each): the relocalizer's "
                          "cv2.BFMatcher(crossCheck=True).match + sort (persistent_map.py:266-270); the RANSAC verification of the top 5 keyframes "
                          "(5 x ~0.3 s per query of 4541 keyframes, < 1 %) is not in this figure; " + ("reference code from baseline/_ref" if rp.kind() == "reference" else "oracle port"))
+    out["sec_per_step_all"] = [round(t, 4) for t in times]
     if a.config in (2, 3):
-        # same work as the GPU unit (every hypothesis scored) on a smaller sample
-        nfull = max(1, min(len(pairs), cores))
-        _, sec_full, _ = rp.run_pairs(pairs[:nfull], workers=cores, full_budget=True, **kw)
         out["value_full_budget"] = nfull / sec_full
         out["sample_full_budget"] = f"{nfull} pairs, all {a.hyps} hypotheses scored (no early exit) = the GPU unit's work (oracle port, vectorised Sampson)"
         # mode (i): one process, OpenCV + BLAS free to use every core (how slam_api calls the path, frame by frame)

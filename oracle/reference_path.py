@@ -159,38 +159,60 @@ def _worker(args):
     return cpu_pair(*args[0], **args[1])
 
 
-def _noop(_):
+def _ready(delay):
+    time.sleep(delay)          # holds the worker long enough that every OTHER worker has to take one of these too
     return os.getpid()
 
 
-def run_pairs(pairs, workers=None, **kw):
-    """Mode (ii): `pairs` (list of (q, t, kq, kt)) on `workers` processes, one OpenCV and one BLAS
-    thread each.  The pool is created, and every worker has imported cv2 / the reference, BEFORE the
-    clock starts.  -> (results, seconds, workers)."""
-    import multiprocessing as mp
+class PairPool:
+    """Mode (ii): a pool of `workers` processes, one OpenCV and one BLAS thread each, created ONCE and reused for every
+    timed step.  `__enter__` returns only when every worker has finished its initializer (imports of cv2 / NumPy / the
+    staged reference): a pool whose stragglers are still importing under the clock reads up to 2x slow."""
 
-    workers = workers or os.cpu_count() or 1
-    jobs = [(p, dict(kw, seed=i)) for i, p in enumerate(pairs)]
-    if workers == 1:
-        saved = {v: os.environ.get(v) for v in _THREAD_VARS}
-        _init_worker()
+    def __init__(self, workers=None):
+        self.workers = workers or os.cpu_count() or 1
+        self.pool = None
+
+    def __enter__(self):
+        import multiprocessing as mp
+
+        if self.workers > 1:
+            # spawn, not fork: the parent may already own CUDA / NCCL state or OpenCV / BLAS thread pools (mode (i)
+            # starts them), and a forked child of a threaded parent deadlocks on their locks
+            self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_init_worker)
+            for _ in range(3):
+                pids = set(self.pool.map(_ready, [0.25] * self.workers, chunksize=1))
+                if len(pids) == self.workers:
+                    break
+        else:
+            self._saved = {v: os.environ.get(v) for v in _THREAD_VARS}
+            _init_worker()
+        return self
+
+    def __exit__(self, *exc):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool.join()
+        else:
+            for v, old in self._saved.items():
+                if old is None:
+                    os.environ.pop(v, None)
+                else:
+                    os.environ[v] = old
+
+    def run(self, pairs, **kw):
+        """-> (results, seconds) for one pass over `pairs`."""
+        jobs = [(p, dict(kw, seed=i)) for i, p in enumerate(pairs)]
         t0 = time.perf_counter()
-        out = [_worker(j) for j in jobs]
-        sec = time.perf_counter() - t0
-        for v, old in saved.items():
-            if old is None:
-                os.environ.pop(v, None)
-            else:
-                os.environ[v] = old
-        return out, sec, 1
-    # spawn, not fork: the parent may already own CUDA / NCCL state or OpenCV / BLAS thread pools (mode (i)
-    # below starts them), and a forked child of a threaded parent deadlocks on their locks
-    with mp.get_context("spawn").Pool(workers, initializer=_init_worker) as pool:
-        pool.map(_noop, range(4 * workers), chunksize=1)
-        t0 = time.perf_counter()
-        out = pool.map(_worker, jobs, chunksize=1)
-        sec = time.perf_counter() - t0
-    return out, sec, workers
+        out = self.pool.map(_worker, jobs, chunksize=1) if self.pool is not None else [_worker(j) for j in jobs]
+        return out, time.perf_counter() - t0
+
+
+def run_pairs(pairs, workers=None, **kw):
+    """One pass over `pairs` (list of (q, t, kq, kt)) on a fresh PairPool.  -> (results, seconds, workers)."""
+    with PairPool(workers) as pool:
+        out, sec = pool.run(pairs, **kw)
+        return out, sec, pool.workers
 
 
 def run_pairs_single_process(pairs, **kw):
