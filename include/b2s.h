@@ -58,6 +58,20 @@ const char* b2s_last_error(void);
 /* sm_count / cc_major / cc_minor / sm clock kHz of the current device. */
 int b2s_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
 
+/* Optional record sink of the winner kernels (HOST struct, passed by pointer; NULL or records == NULL = none): the
+ * kernel that picks the winner also writes the pair's result record (layout: b2s_pack_records below) — no extra
+ * launch at the end of a step.  out_q / out_t / out_d: the selection outputs in the compact layout (pair p at
+ * p * stride); R | t in the record header stay zero (use b2s_pack_records after the pose kernels for those). */
+typedef struct b2s_record_sink {
+  uint8_t* records;      /* device, n_pairs records of record_bytes each */
+  size_t record_bytes;   /* >= b2s_record_bytes(stride), multiple of 16 */
+  const int32_t* out_q;
+  const int32_t* out_t;
+  const int32_t* out_d;
+  int stride;
+  int pair_id0;          /* header pair id = pair_id0 + p */
+} b2s_record_sink;
+
 /* ---- K1/K2: brute-force Hamming kNN-2 + column minimum ------------------------
  * Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) and the two batchDistance
  * passes of BFMatcher(crossCheck=True).match (feature_pipeline.py.bak:68,82,84;
@@ -263,11 +277,13 @@ int b2s_ransac_score_tc(const float* corr, const int32_t* c_off, const int32_t* 
  * Replaces the sequential best/early-exit bookkeeping of homography.py:335-339:
  * best_h = first h with count > 0.8*M if any, else the lowest h among the
  * maximum count; -1 when every count is 0.  inlier_mask[c_off[p]+m] = 1 iff
- * correspondence m is an inlier of hypothesis best_h (float64 arithmetic). */
+ * correspondence m is an inlier of hypothesis best_h (float64 arithmetic).  mask_stride > 0: the kernel also
+ * zeroes inlier_mask[c_off[p] + c_count[p] .. c_off[p] + mask_stride) (the unused tail of a compact slot), so the
+ * caller need not clear the array; sink: see b2s_record_sink. */
 int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c_off,
                       const int32_t* c_count, int n_pairs, const double* E, int H, double th2,
                       const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
-                      uint8_t* inlier_mask, void* stream);
+                      uint8_t* inlier_mask, const b2s_record_sink* sink, int mask_stride, void* stream);
 
 /* ---- result records: what leaves the GPU ------------------------------------------
  * One fixed-size record per pair, written by ONE kernel straight into the buffer that is all-gathered over
@@ -310,7 +326,7 @@ size_t b2s_ransac_winner_workspace_bytes(int n_pairs, int H);
 int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
                               int H, double th2, const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
                               uint8_t* inlier_mask, void* workspace, size_t workspace_bytes, int32_t* counts_out,
-                              int32_t* n_finished_out, void* stream);
+                              int32_t* n_finished_out, const b2s_record_sink* sink, int mask_stride, void* stream);
 
 /* ---- measurement helper ----------------------------------------------------------
  * Saturates one SM pipe with independent instructions to measure its rate:

@@ -31,6 +31,12 @@ PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "
             "vmin_u16x2": 9, "vmin3_u16x2": 10, "viaddmax_u16x2": 11, "setp_sel": 12, "prmt": 13, "ffma2": 14, "ffma2+ffma": 15, "ffma2+2ffma": 16}
 
 
+class RecordSink(C.Structure):
+    """b2s_record_sink (include/b2s.h): the winner kernel also writes the pair's result record."""
+    _fields_ = [("records", C.c_void_p), ("record_bytes", C.c_size_t), ("out_q", C.c_void_p), ("out_t", C.c_void_p),
+                ("out_d", C.c_void_p), ("stride", C.c_int), ("pair_id0", C.c_int)]
+
+
 class B2SError(RuntimeError):
     """libb2s returned a non-zero status."""
 
@@ -107,9 +113,9 @@ def _declare(lib):
     lib.b2s_ransac_winner_workspace_bytes.restype = sz
     lib.b2s_ransac_winner_workspace_bytes.argtypes = [i32, i32]
     lib.b2s_ransac_winner_batched.restype = i32
-    lib.b2s_ransac_winner_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    lib.b2s_ransac_winner_batched.argtypes = [vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp, sz, vp, vp, vp, i32, vp]
     lib.b2s_ransac_select.restype = i32
-    lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp]
+    lib.b2s_ransac_select.argtypes = [vp, vp, vp, vp, i32, vp, i32, dbl, vp, vp, vp, vp, vp, i32, vp]
     lib.b2s_hamming_i8_debug.restype = None
     lib.b2s_hamming_i8_debug.argtypes = [vp, i32]
     lib.b2s_hamming_kernel_timing.restype = i32

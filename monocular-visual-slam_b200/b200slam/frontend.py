@@ -249,8 +249,8 @@ class HammingMatcher:
         oq = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
         ot = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
         od = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
-        cnt = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev)
-        total = torch.zeros(max(b.n_pairs, 1), dtype=torch.int32, device=dev) if with_total else None
+        cnt = torch.empty(max(b.n_pairs, 1), dtype=torch.int32, device=dev)      # the kernel writes every pair's count
+        total = torch.empty(max(b.n_pairs, 1), dtype=torch.int32, device=dev) if with_total else None
         corr = None
         if with_corr:
             if b.kp_q is None or b.kp_t is None:
@@ -381,7 +381,17 @@ class EssentialRansac:
             precision, int(max_m), ptr(counts), current_stream()))
         return counts[:n_pairs, :H]
 
-    def winner(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, return_counts: bool = False):
+    @staticmethod
+    def _sink(sink):
+        """sink = (records tensor [n_pairs, record_bytes], Selection, pair_id0) or None -> (ctypes struct or None, mask_stride)."""
+        if sink is None:
+            return None, 0
+        rec, sel, pid0 = sink
+        st = _capi.RecordSink(rec.data_ptr(), int(rec.shape[-1]), sel.out_q.data_ptr(), sel.out_t.data_ptr(), sel.out_d.data_ptr(),
+                              int(sel.stride), int(pid0))
+        return st, int(sel.stride)
+
+    def winner(self, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, return_counts: bool = False, sink=None):
         """Winner-only scoring (b2s_ransac_winner_batched): best_h / best_count / inlier mask identical to
         score(precision=64) + select, but hypotheses that can neither exceed 0.8 M nor reach the largest complete count
         are abandoned after the first ~3/8 of the correspondences.  return_counts: also (counts [pair, H] — complete
@@ -390,7 +400,8 @@ class EssentialRansac:
         H, dev = E.shape[1], corr.device
         best_h = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=dev)
         best_c = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=dev)
-        mask = torch.zeros(max(corr.shape[0], 1), dtype=torch.uint8, device=dev)
+        st, mstride = self._sink(sink)
+        mask = (torch.empty if mstride else torch.zeros)(max(corr.shape[0], 1), dtype=torch.uint8, device=dev)
         need = int(self._lib.b2s_ransac_winner_workspace_bytes(n_pairs, H))
         if getattr(self, "_win_ws", None) is None or self._win_ws.numel() < need or self._win_ws.device != dev:
             self._win_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
@@ -398,19 +409,24 @@ class EssentialRansac:
         nfin = torch.zeros(max(n_pairs, 1), dtype=torch.int32, device=dev) if return_counts else None
         check(self._lib.b2s_ransac_winner_batched(
             ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2), ptr(th2_per_pair), ptr(best_h), ptr(best_c),
-            ptr(mask), self._win_ws.data_ptr(), need, ptr(counts), ptr(nfin), current_stream()))
+            ptr(mask), self._win_ws.data_ptr(), need, ptr(counts), ptr(nfin), C.byref(st) if st is not None else None, mstride,
+            current_stream()))
         out = (best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]])
         return out + (counts[:n_pairs, :H], nfin[:n_pairs]) if return_counts else out
 
-    def select(self, counts, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None):
+    def select(self, counts, corr, c_off, c_count, n_pairs: int, E, th2: float, th2_per_pair=None, sink=None):
+        """sink = (records, Selection, pair_id0): the winner kernel also writes every pair's result record and clears
+        the unused tail of the inlier mask (no zero-fill, no separate record kernel)."""
         torch = _capi.require_cuda()
         H = E.shape[1]
         best_h = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
         best_c = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=corr.device)
-        mask = torch.zeros(max(corr.shape[0], 1), dtype=torch.uint8, device=corr.device)
+        st, mstride = self._sink(sink)
+        mask = (torch.empty if mstride else torch.zeros)(max(corr.shape[0], 1), dtype=torch.uint8, device=corr.device)
         check(self._lib.b2s_ransac_select(
             ptr(counts), ptr(corr), ptr(c_off), ptr(c_count), n_pairs, ptr(E), H, float(th2),
-            ptr(th2_per_pair), ptr(best_h), ptr(best_c), ptr(mask), current_stream()))
+            ptr(th2_per_pair), ptr(best_h), ptr(best_c), ptr(mask), C.byref(st) if st is not None else None, mstride,
+            current_stream()))
         return best_h[:n_pairs], best_c[:n_pairs], mask[:corr.shape[0]]
 
 
@@ -702,12 +718,15 @@ class Frontend:
         E = self.ransac.hypotheses(sel.corr, sel.c_off, sel.count, b.n_pairs, c.hypotheses,
                                    samples=samples, seed=c.seed, K=K, pair_id0=pair_id0)
         th2 = c.threshold ** 2
+        # without pose recovery the winner kernel itself writes the records (with it, R | t arrive later: pack kernel below)
+        fused = records is not None and not c.with_pose and sel.stride and before_records is None
+        sink = (records, sel, pair_id0) if fused else None
         if c.winner_only:
             counts = None
-            best_h, best_c, mask = self.ransac.winner(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
+            best_h, best_c, mask = self.ransac.winner(sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, sink=sink)
         else:
             counts = self.score(sel, b, E)
-            best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2)
+            best_h, best_c, mask = self.ransac.select(counts, sel.corr, sel.c_off, sel.count, b.n_pairs, E, th2, sink=sink)
         res = FrontendResult(keys, sel, E, counts, best_h, best_c, mask)
         if c.with_pose:      # next-row #2: refit on the winner's inliers + decomposition / cheirality vote (K7)
             if self.pose is None:
@@ -717,7 +736,8 @@ class Frontend:
         if before_records is not None:
             before_records()
         if records is not None:
-            pack_records(records, sel, best_h, best_c, mask, res.R, res.t, n_records=b.n_pairs, pair_id0=pair_id0)
+            if not fused:
+                pack_records(records, sel, best_h, best_c, mask, res.R, res.t, n_records=b.n_pairs, pair_id0=pair_id0)
             res.records = records
         return res
 

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
     const int32_t* __restrict__ counts, const float4* __restrict__ corr, const int32_t* __restrict__ c_off,
     const int32_t* __restrict__ c_count, const double* __restrict__ E, int H, double th2_all,
     const double* __restrict__ th2_pp, int32_t* __restrict__ best_h, int32_t* __restrict__ best_count,
-    uint8_t* __restrict__ mask, const int32_t* __restrict__ early_in, int h_chunk) {
+    uint8_t* __restrict__ mask, const int32_t* __restrict__ early_in, int h_chunk, const b2s_record_sink sink, int mask_stride) {
   __shared__ int s_early;
   __shared__ unsigned long long s_best;
   __shared__ int s_cnt;
@@ -461,11 +461,40 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(
   } else {
     for (int m = tid; m < M; m += blockDim.x) mp[m] = 0;
   }
+  for (int m = M + tid; m < mask_stride; m += blockDim.x) mp[m] = 0;   // the unused tail of the pair's compact slot
   if (mine) atomicAdd(&s_cnt, mine);
   __syncthreads();
   if (tid == 0) {
     best_h[pair] = win;
     best_count[pair] = s_cnt;
+  }
+  if (sink.records) {
+    // the pair's result record, written by the kernel that already holds everything it needs (csrc/records.cu has
+    // the layout and the stand-alone pack kernel used when R | t are appended later): no extra launch at the end of
+    // the step, and this IS the send slice of the all-gather / the source of the step's one device->host copy
+    uint8_t* rec = sink.records + (size_t)pair * sink.record_bytes;
+    const int S = sink.stride;
+    const int raw = c_count[pair], n = min(M, S);
+    if (tid < 16) {
+      int32_t v = 0;
+      if (tid == 0) v = raw;
+      else if (tid == 1) v = win;
+      else if (tid == 2) v = s_cnt;
+      else if (tid == 3) v = sink.pair_id0 + pair;
+      reinterpret_cast<int32_t*>(rec)[tid] = v;   // R | t stay zero: no pose recovery on this path
+    }
+    uint16_t* rq = reinterpret_cast<uint16_t*>(rec + 64);
+    uint16_t* rt = rq + S;
+    uint16_t* rd = rt + S;
+    uint8_t* rm = reinterpret_cast<uint8_t*>(rd + S);
+    const size_t base = (size_t)pair * S;
+    for (int k = tid; k < S; k += blockDim.x) {
+      const bool live = k < n;
+      rq[k] = live ? (uint16_t)sink.out_q[base + k] : (uint16_t)0;
+      rt[k] = live ? (uint16_t)sink.out_t[base + k] : (uint16_t)0;
+      rd[k] = live ? (uint16_t)sink.out_d[base + k] : (uint16_t)0;
+      rm[k] = live ? mp[k] : (uint8_t)0;          // written above by this CTA (the barrier orders it)
+    }
   }
 }
 
@@ -563,6 +592,16 @@ int ransac_score_fp64_cond_launch(const float4* corr, const int32_t* c_off, cons
   return B2S_OK;
 }
 
+static int check_sink(const b2s_record_sink* sink, int mask_stride, b2s_record_sink* out) {
+  B2S_REQUIRE(mask_stride >= 0, "negative mask_stride");
+  if (!sink || !sink->records) return B2S_OK;
+  B2S_REQUIRE(sink->out_q && sink->out_t && sink->out_d && sink->stride > 0, "record sink: selection outputs and stride required");
+  B2S_REQUIRE(sink->record_bytes >= b2s_record_bytes(sink->stride) && (sink->record_bytes & 15u) == 0 &&
+                  ((uintptr_t)sink->records & 15u) == 0, "record sink: record_bytes >= b2s_record_bytes(stride), 16-byte aligned");
+  *out = *sink;
+  return B2S_OK;
+}
+
 }  // namespace b2s
 
 extern "C" {
@@ -642,9 +681,11 @@ size_t b2s_ransac_winner_workspace_bytes(int n_pairs, int H) {
 int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int32_t* c_count, int n_pairs, const double* E,
                               int H, double th2, const double* th2_per_pair, int32_t* best_h, int32_t* best_count,
                               uint8_t* inlier_mask, void* workspace, size_t workspace_bytes, int32_t* counts_out,
-                              int32_t* n_finished_out, void* stream) {
+                              int32_t* n_finished_out, const b2s_record_sink* sink, int mask_stride, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(corr && c_off && c_count && E && best_h && best_count && inlier_mask, "null pointer");
+  b2s_record_sink sk{};
+  if (int rc = check_sink(sink, mask_stride, &sk)) return rc;
   B2S_REQUIRE(n_pairs >= 0 && H >= 0, "negative size");
   B2S_REQUIRE(n_pairs <= 65535, "n_pairs %d exceeds grid.y limit 65535; split the batch", n_pairs);
   if (n_pairs == 0) return B2S_OK;
@@ -683,7 +724,7 @@ int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int
     }
   }
   ransac_select_kernel<<<n_pairs, 256, 0, st>>>(counts, c4, c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count, inlier_mask,
-                                                H > 0 ? early : nullptr, h0);
+                                                H > 0 ? early : nullptr, h0, sk, mask_stride);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;
@@ -691,14 +732,16 @@ int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int
 
 int b2s_ransac_select(const int32_t* counts, const float* corr, const int32_t* c_off, const int32_t* c_count,
                       int n_pairs, const double* E, int H, double th2, const double* th2_per_pair, int32_t* best_h,
-                      int32_t* best_count, uint8_t* inlier_mask, void* stream) {
+                      int32_t* best_count, uint8_t* inlier_mask, const b2s_record_sink* sink, int mask_stride, void* stream) {
   using namespace b2s;
   B2S_REQUIRE(counts && corr && c_off && c_count && E && best_h && best_count && inlier_mask, "null pointer");
+  b2s_record_sink sk{};
+  if (int rc = check_sink(sink, mask_stride, &sk)) return rc;
   B2S_REQUIRE(n_pairs >= 0 && H >= 0, "negative size");
   if (n_pairs == 0) return B2S_OK;
   ransac_select_kernel<<<n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       counts, reinterpret_cast<const float4*>(corr), c_off, c_count, E, H, th2, th2_per_pair, best_h, best_count,
-      inlier_mask, nullptr, 0);
+      inlier_mask, nullptr, 0, sk, mask_stride);
   B2S_CUDA(cudaGetLastError());
   note_launch();
   return B2S_OK;

@@ -24,13 +24,17 @@ def _seq_batch(F, N, seed, counts=None):
     return b, desc, kp
 
 
-def test_records_equal_the_separate_result_arrays():
+@pytest.mark.parametrize("with_pose,winner_only", [(True, False), (False, False), (False, True)],
+                         ids=["pack_kernel_with_pose", "fused_into_winner_kernel", "fused_winner_only"])
+def test_records_equal_the_separate_result_arrays(with_pose, winner_only):
+    """Both ways a record is written: by the winner kernel itself (no pose recovery: no extra launch) and by the
+    stand-alone pack kernel after the pose kernels."""
     import torch
     from b200slam.frontend import Frontend, FrontendConfig, record_bytes, unpack_records
     S = 300
     counts = np.array([700, 650, 700, 1, 700, 699, 12], np.int32)
     b, _, _ = _seq_batch(7, 700, 21, counts)
-    fe = Frontend(FrontendConfig(hypotheses=256, max_matches=S, with_pose=True))
+    fe = Frontend(FrontendConfig(hypotheses=256, max_matches=S, with_pose=with_pose, winner_only=winner_only))
     rec = torch.full((b.n_pairs, record_bytes(S)), 0xAB, dtype=torch.uint8, device="cuda")
     res = fe.run(b, records=rec, pair_id0=40)
     torch.cuda.synchronize()
@@ -40,8 +44,12 @@ def test_records_equal_the_separate_result_arrays():
     np.testing.assert_array_equal(u["best_h"], res.best_h.cpu().numpy())
     np.testing.assert_array_equal(u["inliers"], res.best_count.cpu().numpy())
     np.testing.assert_array_equal(u["pair_id"], 40 + np.arange(b.n_pairs))
-    np.testing.assert_array_equal(u["R"].reshape(-1, 9), res.R.cpu().numpy().astype(np.float32))
-    np.testing.assert_array_equal(u["t"], res.t.cpu().numpy().astype(np.float32))
+    if with_pose:
+        np.testing.assert_array_equal(u["R"].reshape(-1, 9), res.R.cpu().numpy().astype(np.float32))
+        np.testing.assert_array_equal(u["t"], res.t.cpu().numpy().astype(np.float32))
+    else:
+        assert not u["R"].any() and not u["t"].any()
+    assert not res.inlier_mask.cpu().numpy().reshape(b.n_pairs, S)[np.arange(S)[None] >= cnt[:, None]].any()   # unused tails cleared
     oq, ot, od, mk = (x.cpu().numpy().reshape(b.n_pairs, S) for x in (res.sel.out_q, res.sel.out_t, res.sel.out_d, res.inlier_mask))
     for p in range(b.n_pairs):
         c = int(cnt[p])
