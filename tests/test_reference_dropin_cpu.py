@@ -48,7 +48,10 @@ def test_install_rebinds_importers_regardless_of_import_order():
 @pytest.mark.parametrize("test_file", ["test_slam_api.py", "test_feature_control_plane.py", "test_tracking_control_plane.py"])
 def test_reference_tests_pass_with_the_bridge(test_file, tmp_path):
     env = dict(os.environ, PYTHONPATH=f"{ROOT}{os.pathsep}{REF}", PYTHONDONTWRITEBYTECODE="1")
-    for attempt in range(3):        # the reference's control-plane tests are timing-sensitive on a loaded box
+    import time
+    for attempt in range(6):        # the reference's control-plane tests are timing-sensitive on a loaded box
+        if attempt:
+            time.sleep(3.0)
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(REF / "tests" / test_file),
                             "--rootdir", str(tmp_path)], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
         if r.returncode == 0:
