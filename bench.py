@@ -530,6 +530,17 @@ def stage_times(env, fe, b, pose_rec=None, reps=10):
     return out
 
 
+def hamming_variants(env, batch, steps=5):
+    """Whole-call time (ms) of the three Hamming kernels on `batch` — the K1-vs-K2 decision record at this shape."""
+    from b200slam.frontend import HammingMatcher
+    out = {}
+    for name, vid in env.variants.items():
+        m = HammingMatcher(variant=vid)
+        out[name] = float(np.mean(env.timed(lambda: m.knn2(batch), steps, 2)))
+        del m
+    return out
+
+
 def measured_peaks(env):
     from b200slam.frontend import mma_microbench, pipe_microbench
 
@@ -955,6 +966,7 @@ def run_config4(env, a, peaks=None, brief=False):
         peaks = measured_peaks(env)
     hr = hamming_roofline(env, fe.matcher, batch, float(P) * a.nfeat * a.nfeat, a.steps, peaks)
     hr1 = hamming_roofline(env, fe.matcher, one, float(a.nfeat) * a.nfeat, a.steps, peaks)
+    variants_ms = hamming_variants(env, batch, 3) if not brief else None
 
     stages = stage_times(env, fe, batch)
     stages["lone_pair"] = stage_times(env, fe, one)
@@ -982,7 +994,8 @@ def run_config4(env, a, peaks=None, brief=False):
     clk = clocks.stop() if (rank == 0 and not brief) else None
     if rank != 0:
         return None
-    roof = _roof_from(hr, peaks, "hamming_knn2_i8s_kernel", extra={"lone_pair": {k: hr1[k] for k in ("kernel_ms", "call_ms", "achieved_top_s", "frac_of_int8_peak", "plan")}})
+    roof = _roof_from(hr, peaks, "hamming_knn2_i8s_kernel", extra={"lone_pair": {k: hr1[k] for k in ("kernel_ms", "call_ms", "achieved_top_s", "frac_of_int8_peak", "plan")},
+                                                                    "hamming_variants_ms": variants_ms})
     e2e = {"value": world * P * n_e2e / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * a.sub_batches,
            "d2h_bytes_per_step": pipe.d2h_bytes * a.sub_batches, "api": "b200slam.frontend.PairPipeline.submit / result", "steps_in_flight": depth,
            "ms_per_step": e2e_total / n_e2e * a.sub_batches}
@@ -1053,6 +1066,7 @@ def run_config5(env, a, peaks=None, brief=False):
     m = sw.sweep
     hr = hamming_roofline(env, m.matcher, m._batch(N), float(hi - lo) * N * N, a.steps, peaks, need_second=False)   # the sweep's kernel: cross-check only
     hr_full = hamming_roofline(env, m.matcher, m._batch(N), float(hi - lo) * N * N, max(3, a.steps // 2), peaks)
+    variants_ms = hamming_variants(env, m._batch(N), 3) if not brief else None
 
     # e2e: the query frame arrives from pinned host memory (80 KB), the gathered candidate records + per-keyframe counts go back
     out_host = torch.empty(sw.gather.buf.shape, dtype=torch.uint8).pin_memory()
@@ -1074,7 +1088,8 @@ def run_config5(env, a, peaks=None, brief=False):
              "planted_keyframe": best, "planted_found_first": bool(len(cand["pair_id"]) and int(cand["pair_id"][0]) == best),
              "mean_matches_per_keyframe": float(np.mean(counts))}
     roof = _roof_from(hr, peaks, "hamming_knn2_i8s_kernel<1, false, 2, false> (best neighbour only: BFMatcher(crossCheck=True).match never reads the second)",
-                      extra={"with_second_neighbour": {k: hr_full[k] for k in ("kernel_ms", "achieved_top_s", "frac_of_int8_peak")}})
+                      extra={"with_second_neighbour": {k: hr_full[k] for k in ("kernel_ms", "achieved_top_s", "frac_of_int8_peak")},
+                             "hamming_variants_ms": variants_ms})
     e2e = {"value": n_kf * len(e2e_ms) / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(N * 40), "d2h_bytes_per_step": int(out_host.numel()),
            "api": "b200slam.sharding.ShardedSweep.query / result_host", "ms_per_step": e2e_total / len(e2e_ms)}
     return _base_line(env, a, value, total_ms, "strong", clk, roof, e2e, {}, launches,
