@@ -330,7 +330,8 @@ int b2s_ransac_winner_batched(const float* corr, const int32_t* c_off, const int
 
 /* ---- measurement helper ----------------------------------------------------------
  * Saturates one SM pipe with independent instructions to measure its rate:
- * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD, 7 REDUX.MIN, 8 SHFL.
+ * which = 0 POPC, 1 LOP3, 2 IADD3, 3 IMNMX, 4 DFMA, 5 FFMA, 6 IMAD, 7 REDUX.MIN, 8 SHFL, 9-13 packed 16-bit min/max,
+ * SEL, PRMT, 14 FFMA2 (fma.rn.f32x2), 15-19 FFMA2 mixed with FFMA / IADD3 (one group counts as one instruction).
  * Launches ctas_per_sm*SMs CTAs of 256 threads doing `iters` x 64 instructions per
  * thread; *ops_out = total thread-level instructions executed (the caller times it). */
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink,

@@ -106,6 +106,18 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
           asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(f[(k + 1) & 7]));
           asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(g[k]) : "f"(g[(k + 1) & 7]));
         }
+        if (WHICH == 17) {  // one FFMA2 + one ALU-pipe add: does the half-rate packed FMA leave its second issue cycle to another pipe?
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(c1));
+        }
+        if (WHICH == 18) {  // one FFMA2 + two ALU-pipe adds
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(c1));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[(k + 3) & 7]) : "r"(c2));
+        }
+        if (WHICH == 19) {  // FFMA2 with three distinct 64-bit sources (register-file read bandwidth)
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]), "l"(p2[(k + 2) & 7]));
+        }
       }
     }
   }
@@ -227,7 +239,7 @@ int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink,
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(which >= 0 && which <= 16, "which must be 0..16");
+  B2S_REQUIRE(which >= 0 && which <= 19, "which must be 0..19");
   B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
   const int grid = sm_count() * ctas_per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -247,6 +259,9 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     case 13: pipe_kernel<13><<<grid, 256, 0, st>>>(iters, sink); break;
     case 14: pipe_kernel<14><<<grid, 256, 0, st>>>(iters, sink); break;
     case 15: pipe_kernel<15><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 17: pipe_kernel<17><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 18: pipe_kernel<18><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 19: pipe_kernel<19><<<grid, 256, 0, st>>>(iters, sink); break;
     case 16: pipe_kernel<16><<<grid, 256, 0, st>>>(iters, sink); break;
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }

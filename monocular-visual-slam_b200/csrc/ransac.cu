@@ -11,6 +11,8 @@
 // this costs ~1 us per 2000x500 pair); a float32 scoring variant exists for comparison.
 // The inlier test is the division-free form  num^2 < th^2 * den  of the reference's
 // num^2 / den < th^2  (den = 0 -> never an inlier in both).
+#include <type_traits>
+
 #include "common.cuh"
 #include "linalg.cuh"
 #include "sampson.cuh"
@@ -84,6 +86,36 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 constexpr int kScoreHThreads = 128;
 constexpr int kScoreHChunk = 512;   // 8 KB of shared memory: the usual pair (<= 500 correspondences) is staged once, in the pass that also finds W1 / W2
 
+// B2S_K3H_PACK2: a thread evaluates TWO correspondences per step on packed fma.rn.f32x2 (SASS FFMA2): the same 19
+// float32 operations per evaluation in the same order (identical values, identical band), half the issue slots.
+// Shared memory then holds correspondences 2k and 2k+1 as (x0, x1, y0, y1) (u0, u1, v0, v1), so that one
+// LDS.128 delivers two aligned register pairs and the loop needs no register moves.
+#ifndef B2S_K3H_PACK2
+#define B2S_K3H_PACK2 1
+#endif
+// B2S_K3H_GROUPS: blocks of 32 evaluations between two passes over the undecidable ones (1, 2 or 4).
+#ifndef B2S_K3H_GROUPS
+#define B2S_K3H_GROUPS 2
+#endif
+constexpr int kK3hGroups = B2S_K3H_GROUPS;
+constexpr int kK3hSpan = 32 * kK3hGroups;
+__device__ __forceinline__ void k3h_stage(float4* s_p, int m, const float4 c) {
+#if B2S_K3H_PACK2
+  float* f = reinterpret_cast<float*>(s_p) + (m >> 1) * 8 + (m & 1);
+  f[0] = c.x; f[2] = c.y; f[4] = c.z; f[6] = c.w;
+#else
+  s_p[m] = c;
+#endif
+}
+__device__ __forceinline__ float4 k3h_staged(const float4* s_p, int m) {
+#if B2S_K3H_PACK2
+  const float* f = reinterpret_cast<const float*>(s_p) + (m >> 1) * 8 + (m & 1);
+  return make_float4(f[0], f[2], f[4], f[6]);
+#else
+  return s_p[m];
+#endif
+}
+
 // Winner-only scoring (b2s_ransac_winner_batched) evaluates a hypothesis in two pieces: every hypothesis on the
 // first screen_len(M) correspondences, and only those that can still win on the rest.
 __host__ __device__ inline int screen_len(int M) { return M <= 64 ? M : min(M, ((3 * M) / 8 + 31) & ~31); }
@@ -92,8 +124,11 @@ __host__ __device__ inline int screen_len(int M) { return M <= 64 ? M : min(M, (
 // MODE 1: the screening prefix [0, screen_len(M)), counts written.
 // MODE 2: the rest [screen_len(M), M) for the hypotheses listed in `list` (n_list[pair] of them per pair), added
 //         to the count the screening pass left (single writer per hypothesis).
+#ifndef B2S_K3H_MIN_CTAS
+#define B2S_K3H_MIN_CTAS 7   // 72 registers; left to itself ptxas takes 140-200 for the unrolled spans and runs 10 % slower
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
+__global__ void __launch_bounds__(kScoreHThreads, B2S_K3H_MIN_CTAS) ransac_score_hybrid_kernel(
     const float4* __restrict__ corr, const int32_t* __restrict__ c_off, const int32_t* __restrict__ c_count,
     const double* __restrict__ E, int H, double th2_all, const double* __restrict__ th2_pp,
     int32_t* __restrict__ counts, const int32_t* __restrict__ list, const int32_t* __restrict__ n_list,
@@ -152,14 +187,14 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
     float w1 = 0.0f, w2 = 0.0f;
     for (int m = threadIdx.x; m < M; m += kScoreHThreads) {
       const float4 c = __ldg(cp + m);
-      if (m < kScoreHChunk) s_p[m] = c;   // the first chunk is staged by the same pass
+      if (m < kScoreHChunk) k3h_stage(s_p, m, c);   // the first chunk is staged by the same pass
       w1 = fmaxf(w1, fmaf(c.x, c.x, fmaf(c.y, c.y, 1.0f)));
       w2 = fmaxf(w2, fmaf(c.z, c.z, fmaf(c.w, c.w, 1.0f)));
     }
     {  // NaN padding of the first chunk's last group (see the chunk loop)
       const int n0 = min(kScoreHChunk, M), n0_32 = (n0 + 31) & ~31;
       const float qn = __int_as_float(0x7FC00000);
-      for (int m = n0 + threadIdx.x; m < n0_32; m += kScoreHThreads) s_p[m] = make_float4(qn, qn, qn, qn);
+      for (int m = n0 + threadIdx.x; m < n0_32; m += kScoreHThreads) k3h_stage(s_p, m, make_float4(qn, qn, qn, qn));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -198,6 +233,12 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
   // every warp diverge on ~6 % of its steps — 32 lanes x 1.8e-3 on tracking data — and each detour
   // is a ~25-deep dependent DFMA chain: 0.40 ms per bench step, against 0.30 ms this way.)
   const float qnan = __int_as_float(0x7FC00000);
+#if B2S_K3H_PACK2
+  float2 e2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) e2[k] = make_float2(e[k], e[k]);
+  const float2 nth2_2 = make_float2(-th2, -th2), ntwo_delta2 = make_float2(-two_delta, -two_delta), nkappa2 = make_float2(-kappa0, -kappa0);
+#endif
   int count = 0;
   for (int base = 0; base < M; base += kScoreHChunk) {
     const int n = min(kScoreHChunk, M - base);
@@ -206,43 +247,97 @@ __global__ void __launch_bounds__(kScoreHThreads) ransac_score_hybrid_kernel(
       __syncthreads();
       // the tail of the last group is padded with NaN: never a certain inlier, and its bits are masked off
       for (int m = threadIdx.x; m < n32; m += kScoreHThreads)
-        s_p[m] = m < n ? __ldg(cp + base + m) : make_float4(qnan, qnan, qnan, qnan);
+        k3h_stage(s_p, m, m < n ? __ldg(cp + base + m) : make_float4(qnan, qnan, qnan, qnan));
       __syncthreads();
     }
-    for (int m0 = 0; m0 < n32; m0 += 32) {
-      uint32_t band = 0u;
+    auto span = [&](auto gc, const int m0) {
+      constexpr int G = decltype(gc)::value;
+      uint32_t band[G];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float4 c = s_p[m0 + j];
-        const float a0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
-        const float a1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
-        const float a2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
-        const float b0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
-        const float b1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
-        const float num = fmaf(c.z, a0, fmaf(c.w, a1, a2));
-        const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
-        const float T = th2 * den;
-        const float d = fmaf(num, num, -T);                              // one rounding fewer than the bound allows for
-        const float B = fmaf(two_delta, fabsf(num), kappa0);             // see the notes on q + T and on T <= Tmax above the loop
-        // count += d < -B (certain inlier); band |= bit unless |d| > B (undecidable in float32, or not
-        // finite).  Two predicated instructions; the compiler's own form took 3.5 per step.
-        asm("{\n\t.reg .pred p, q;\n\t"
-            "setp.lt.f32 p, %2, %3;\n\t"
-            "@p add.s32 %0, %0, 1;\n\t"
-            "setp.gt.f32 q, %4, %5;\n\t"
-            "@!q or.b32 %1, %1, %6;\n\t}"
-            : "+r"(count), "+r"(band)
-            : "f"(d), "f"(-B), "f"(fabsf(d)), "f"(B), "r"(1u << j));
+      for (int g = 0; g < G; ++g) {
+        const int mg = m0 + 32 * g;
+        band[g] = 0u;
+#if B2S_K3H_PACK2
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 xy = s_p[mg + 2 * j], uv = s_p[mg + 2 * j + 1];
+          const float2 x = make_float2(xy.x, xy.y), y = make_float2(xy.z, xy.w);
+          const float2 u = make_float2(uv.x, uv.y), v = make_float2(uv.z, uv.w);
+          const float2 a0 = __ffma2_rn(e2[0], x, __ffma2_rn(e2[1], y, e2[2]));
+          const float2 a1 = __ffma2_rn(e2[3], x, __ffma2_rn(e2[4], y, e2[5]));
+          const float2 a2 = __ffma2_rn(e2[6], x, __ffma2_rn(e2[7], y, e2[8]));
+          const float2 b0 = __ffma2_rn(e2[0], u, __ffma2_rn(e2[3], v, e2[6]));
+          const float2 b1 = __ffma2_rn(e2[1], u, __ffma2_rn(e2[4], v, e2[7]));
+          const float2 num = __ffma2_rn(u, a0, __ffma2_rn(v, a1, a2));
+          const float2 den = __ffma2_rn(a0, a0, __ffma2_rn(a1, a1, __ffma2_rn(b0, b0, __fmul2_rn(b1, b1))));
+          const float2 nT = __fmul2_rn(nth2_2, den);                          // -(th^2 den): the sign costs no rounding
+          const float2 d = __ffma2_rn(num, num, nT);
+          const float2 nB = __ffma2_rn(ntwo_delta2, make_float2(fabsf(num.x), fabsf(num.y)), nkappa2);   // -B
+          asm("{\n\t.reg .pred p, q;\n\t"
+              "setp.lt.f32 p, %2, %3;\n\t"
+              "@p add.s32 %0, %0, 1;\n\t"
+              "setp.gt.f32 q, %4, %5;\n\t"
+              "@!q or.b32 %1, %1, %6;\n\t}"
+              : "+r"(count), "+r"(band[g])
+              : "f"(d.x), "f"(nB.x), "f"(fabsf(d.x)), "f"(-nB.x), "r"(1u << (2 * j)));
+          asm("{\n\t.reg .pred p, q;\n\t"
+              "setp.lt.f32 p, %2, %3;\n\t"
+              "@p add.s32 %0, %0, 1;\n\t"
+              "setp.gt.f32 q, %4, %5;\n\t"
+              "@!q or.b32 %1, %1, %6;\n\t}"
+              : "+r"(count), "+r"(band[g])
+              : "f"(d.y), "f"(nB.y), "f"(fabsf(d.y)), "f"(-nB.y), "r"(2u << (2 * j)));
+        }
+#else
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 c = s_p[mg + j];
+          const float a0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
+          const float a1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
+          const float a2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
+          const float b0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
+          const float b1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
+          const float num = fmaf(c.z, a0, fmaf(c.w, a1, a2));
+          const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+          const float T = th2 * den;
+          const float d = fmaf(num, num, -T);                              // one rounding fewer than the bound allows for
+          const float B = fmaf(two_delta, fabsf(num), kappa0);             // see the notes on q + T and on T <= Tmax above the loop
+          // count += d < -B (certain inlier); band |= bit unless |d| > B (undecidable in float32, or not
+          // finite).  Two predicated instructions; the compiler's own form took 3.5 per step.
+          asm("{\n\t.reg .pred p, q;\n\t"
+              "setp.lt.f32 p, %2, %3;\n\t"
+              "@p add.s32 %0, %0, 1;\n\t"
+              "setp.gt.f32 q, %4, %5;\n\t"
+              "@!q or.b32 %1, %1, %6;\n\t}"
+              : "+r"(count), "+r"(band[g])
+              : "f"(d), "f"(-B), "f"(fabsf(d)), "f"(B), "r"(1u << j));
+        }
+#endif
+        const int left = n - mg;
+        if (left < 32) band[g] &= left > 0 ? (1u << left) - 1u : 0u;
       }
-      const int left = n - m0;
-      if (left < 32) band &= (1u << left) - 1u;
-      while (band) {  // the float64 expression of K3 decides
-        const int j = __ffs((int)band) - 1;
-        band &= band - 1u;
-        const float4 c = s_p[m0 + j];
+      // The float64 expression of K3 decides.  One pass per 32 G evaluations: a warp walks max-over-lanes set bits,
+      // and the undecidable evaluations (~2 per 1024) of a longer span mostly sit on different lanes.
+      uint64_t lo = band[0], hi = 0;
+      if (G > 1) lo |= (uint64_t)band[G > 1 ? 1 : 0] << 32;
+      if (G > 2) hi = band[G > 2 ? 2 : 0] | ((uint64_t)band[G > 2 ? 3 : 0] << 32);
+      while (lo | hi) {
+        int j;
+        if (lo) {
+          j = __ffsll((long long)lo) - 1;
+          lo &= lo - 1;
+        } else {
+          j = 64 + __ffsll((long long)hi) - 1;
+          hi &= hi - 1;
+        }
+        const float4 c = k3h_staged(s_p, m0 + j);
         count += sampson_inlier<double>(ed, (double)c.x, (double)c.y, (double)c.z, (double)c.w, th2d) ? 1 : 0;
       }
-    }
+    };
+    int m0 = 0;
+    for (; m0 + kK3hSpan <= n32; m0 += kK3hSpan) span(std::integral_constant<int, kK3hGroups>{}, m0);
+    if (kK3hGroups > 1)
+      for (; m0 < n32; m0 += 32) span(std::integral_constant<int, 1>{}, m0);   // what is left of the chunk, one group at a time
   }
   if (live) {
     if (MODE == 2) counts[(size_t)pair * H + h] += count;

@@ -47,7 +47,7 @@ def test_sass_is_blackwell_native():
     """The built library carries sm_100a code, and the SHIPPED Hamming kernel itself — not just some kernel of the
     library — issues tcgen05.mma kind::i8 (SASS UTCIMMA), reads its accumulators from TMEM (LDTM), commits to
     mbarriers (UTCBAR) and stages operands with the TMA engine's bulk copies (UBLKCP); the tensor-core scoring kernel
-    issues UTCHMMA; the POPC kernel keeps POPC + REDUX.  profiles/r02_sass.md is the committed listing (tools/sass_evidence.py)."""
+    issues UTCHMMA; the POPC kernel keeps POPC + REDUX; the scoring kernel runs on packed FFMA2.  profiles/r02_sass.md is the committed listing (tools/sass_evidence.py)."""
     import shutil
     import subprocess
     from b200slam import _capi
@@ -78,7 +78,8 @@ def test_sass_is_blackwell_native():
     assert "UTCHMMA" in k3t and "LDTM" in k3t
     k1 = body("hamming_knn2_popc_kernel")
     assert "POPC" in k1 and "REDUX" in k1 and "UBLKCP" in k1
-    assert "DFMA" in body("ransac_score_hybrid_kernel") and "FFMA" in body("ransac_score_hybrid_kernel")
+    k3h = body("ransac_score_hybrid_kernel")
+    assert "DFMA" in k3h and k3h.count("FFMA2") >= 16 * 17              # packed fma.rn.f32x2: two correspondences per instruction
 
 
 def test_product_fails_loudly_without_cuda():
