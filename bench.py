@@ -548,7 +548,7 @@ def measured_peaks(env):
     mp = json.loads(mp_path.read_text()) if mp_path.exists() else {}
     peaks = {"i8": mma_microbench(), "bf16": float(mp.get("bf16_tflops", 1590.0)), "hbm": float(mp.get("hbm_gbs", 6650.0)),
              "src": "MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)"}
-    for name in ("popc", "lop3", "imnmx", "imad", "dfma", "ffma", "shfl"):
+    for name in ("popc", "lop3", "imnmx", "imad", "dfma", "ffma", "shfl", "ffma2"):
         peaks[name] = pipe_microbench(name)
     return peaks
 
@@ -797,13 +797,17 @@ def run_config2(env, a):
                                   "Kept as the integer-pipe baseline of the K1-vs-K2 decision."},
             "hbm": {"bound": "hbm", "achieved": alg_bytes / t_i8 / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": alg_bytes / t_i8 / 1e9 / peaks["hbm"],
                     "peak_source": peaks["src"], "note": "not the binding roofline: 210 POPC per byte (SURVEY 8d)"},
-            "ransac_score": {"bound": "fp32-fma-pipe", "achieved": 22.0 * P * a.hyps * 500.0 / (stages["score"] * 1e-3) / 1e12,
-                             "peak": peaks["ffma"] / 1e12, "unit": "T FFMA-class instr/s",
-                             "frac": 22.0 * P * a.hyps * 500.0 / (stages["score"] * 1e-3) / peaks["ffma"], "kernel": "ransac_score_hybrid_kernel",
-                             "kernel_ms": stages["score"],
-                             "note": "K3h: 22 FFMA/FMUL + 2 FSETP + 2 predicated integer ops + 1 LDS.128 per (hypothesis, correspondence) in float32, "
-                                     "M = 500; evaluations inside the rounding band (~2e-3) are redone in float64, so the counts are the float64 kernel's"},
-            "pipe_rates_per_clk_per_sm": {k: peaks[k] / sms / (clock_khz * 1e3) for k in ("popc", "lop3", "imnmx", "imad", "dfma", "ffma", "shfl")}})
+            "ransac_score": {"bound": "fp32-fma-pipe (packed FFMA2: register-file reads of three-operand instructions)",
+                             "achieved": 19.0 * P * a.hyps * 500.0 / (stages["score"] * 1e-3) / 1e12,
+                             "peak": 2.0 * peaks["ffma2"] / 1e12, "unit": "T float32 FMA/s",
+                             "frac": 19.0 * P * a.hyps * 500.0 / (stages["score"] * 1e-3) / (2.0 * peaks["ffma2"]), "kernel": "ransac_score_hybrid_kernel",
+                             "kernel_ms": stages["score"], "peak_scalar_ffma": peaks["ffma"] / 1e12,
+                             "note": "K3h: 19 float32 FMA-class operations per (hypothesis, correspondence), issued as fma.rn.f32x2 on two "
+                                     "correspondences at once (9.5 FFMA2 + 2 FSETP + 2 predicated integer ops + 0.5 LDS.128 per evaluation), M = 500; "
+                                     "peak = 2 x the measured FFMA2 issue rate with two distinct register-pair sources (an FFMA2 with three distinct "
+                                     "pairs issues at 2/3 of it: tools/pipe_rates.py); evaluations inside the rounding band (~2e-3) are redone in "
+                                     "float64, so the counts are the float64 kernel's"},
+            "pipe_rates_per_clk_per_sm": {k: peaks[k] / sms / (clock_khz * 1e3) for k in ("popc", "lop3", "imnmx", "imad", "dfma", "ffma", "ffma2", "shfl")}})
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * a.sub_batches, "d2h_bytes_per_step": pipe.d2h_bytes * a.sub_batches,
            "api": "b200slam.frontend.SequencePipeline.submit / result (one library call per launch set)", "schedule": a.e2e_schedule,
            "cuda_graph": pipe.use_graph, "steps_in_flight": depth, "d2h_copies_per_launch_set": 1,
@@ -822,6 +826,9 @@ def run_config2(env, a):
              "value_with_pose": value_pose,
              "value_with_pose_note": "same step + n-point refit of E on the winner's inliers + decomposition / cheirality vote (K7), R | t in the records; "
                                      "outside the metric's unit (SURVEY 8d), reported beside it",
+             "stream_lanes": sf.lanes,
+             "stream_lanes_note": "the launch sets of a step alternate between this many streams inside the step's CUDA graph (own workspaces "
+                                  "per lane): tails, one-CTA-per-pair kernels and launch gaps of one set are filled by the next",
              "record_bytes_per_pair": sf.rec_bytes, "collectives_per_step": 1 if world > 1 else 0,
              "collective_schedule": ("the all-gather of step s is a node of step s + 1's graph, started after its first selection kernel and joined before "
                                      "its first record kernel (under the 8-point / scoring kernels)") if (world > 1 and sf.pipelined) else ("after the step's last launch set" if world > 1 else None),

@@ -29,7 +29,8 @@ HAMMING_BEST_ONLY = 0x100      # OR-ed into the variant: fwd_second not needed (
 
 PIPE_IDS = {"popc": 0, "lop3": 1, "iadd": 2, "imnmx": 3, "dfma": 4, "ffma": 5, "imad": 6, "redux": 7, "shfl": 8,
             "vmin_u16x2": 9, "vmin3_u16x2": 10, "viaddmax_u16x2": 11, "setp_sel": 12, "prmt": 13, "ffma2": 14, "ffma2+ffma": 15, "ffma2+2ffma": 16,
-            "ffma2+iadd": 17, "ffma2+2iadd": 18, "ffma2_3src": 19}
+            "ffma2+iadd": 17, "ffma2+2iadd": 18, "ffma2_3src": 19,
+            "ffma2_s_p_p": 20, "ffma2_s_p_s": 21, "ffma_3src": 22, "ffma2_p_p_q": 23, "ffma2_s_p_samep": 24}
 
 
 class RecordSink(C.Structure):

@@ -126,6 +126,9 @@ class RecordGather:
         return torch.cat(parts, dim=0)
 
 
+DEFAULT_LANES = 3    # measured on the metric's step (tools/lanes_ab.py): 1 lane 473.5 k pairs/s, 2 lanes 488.7 k, 3 lanes 494.8 k
+
+
 class ShardedFrontend:
     """The hot path on this rank's block of a global pair batch + the gather of every rank's result records.
 
@@ -144,12 +147,14 @@ class ShardedFrontend:
     one-CTA-per-SM Hamming kernel that follows it, whose late CTAs then finish late), one collective per batch 0.969,
     pipelined under the RANSAC kernels: see that file.
 
+    ``lanes`` (default 3): the launch sets of a batch alternate between that many streams, see __init__.
+
     ``capture(batches)`` records a whole batch — collective included — into ONE CUDA graph (``replay()``); if the
     NCCL build cannot be captured the kernels are replayed and the collective is issued eagerly (``gather_in_graph``
     says which).  ``records()`` -> device uint8 [sets_per_gather, n_pairs_global, record_bytes]."""
 
     def __init__(self, cfg, n_pairs_global: int, *, variant=None, group=None, device=None, sets_per_gather: int = 1,
-                 pipelined: bool = True):
+                 pipelined: bool = True, lanes: int | None = None):
         import os
 
         from . import _capi
@@ -160,7 +165,14 @@ class ShardedFrontend:
             raise ValueError("ShardedFrontend needs max_matches (record stride)")
         self.cfg = cfg            # cfg.with_pose decides whether the records carry R | t (else zeros)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.fe = Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant)
+        # lanes: the launch sets of a batch alternate between `lanes` streams (each with its own Frontend = its own
+        # workspaces), so the tail of one set's kernels, its one-CTA-per-pair selection / winner kernels and the gaps
+        # between dependent launches are filled with the other set's work.  Lane 0 is the caller's stream; the side
+        # lanes fork from it at their first launch set of a batch and join it behind the last (also under capture).
+        self.lanes = max(1, min(int(os.environ.get("B2S_LANES", 0)) or (DEFAULT_LANES if lanes is None else int(lanes)), max(1, int(sets_per_gather))))
+        self.fes = [Frontend(self.cfg, variant=_capi.VARIANT_I8MMA1 if variant is None else variant) for _ in range(self.lanes)]
+        self.fe = self.fes[0]
+        self._side = [torch.cuda.Stream(device=self.dev) for _ in range(self.lanes - 1)]
         self.rec_bytes = record_bytes(cfg.max_matches)
         self.sets = max(1, int(sets_per_gather))
         self.n_pairs_global = int(n_pairs_global)
@@ -178,7 +190,7 @@ class ShardedFrontend:
         else:
             self.send = self.gather.local               # in-place: the send slice of the gather buffer itself
         self.lo, self.hi = shard_bounds(self.n_pairs_global, self.rank, self.world)
-        self._work, self._k, self._pending = None, 0, False
+        self._work, self._k, self._pending, self._kernels_only = None, 0, False, False
         self._graph, self.res = None, None
         self.gather_in_graph = False
 
@@ -200,14 +212,31 @@ class ShardedFrontend:
         j = self._k % self.sets
         self._k += 1
         rows = self.send[j * self.cap: j * self.cap + batch.n_pairs]
-        first = j == 0 and self.pipelined and self.world > 1 and self._pending
-        # pipelined: the previous batch's records (still in `send`) leave while this set's RANSAC kernels run; the
-        # record kernel of this set, which overwrites the first rows of `send`, waits for the collective
-        self.res = self.fe.run(batch, K=K, records=rows, pair_id0=self.lo,
-                               after_select=self._start_gather if first else None,
-                               before_records=self._join_gather if first else None)
+        first = j == 0 and self.pipelined and self.world > 1 and self._pending and not self._kernels_only
+        lane = j % self.lanes
+        if lane == 0:
+            # pipelined: the previous batch's records (still in `send`) leave while this set's RANSAC kernels run; the
+            # record kernel of this set, which overwrites the first rows of `send`, waits for the collective
+            self.res = self.fes[0].run(batch, K=K, records=rows, pair_id0=self.lo,
+                                       after_select=self._start_gather if first else None,
+                                       before_records=self._join_gather if first else None)
+        else:
+            import torch
+
+            side = self._side[lane - 1]
+            if j < self.lanes:                      # fork: behind everything the caller's stream holds so far — set 0
+                side.wait_stream(torch.cuda.current_stream(self.dev))   # included, i.e. behind the join of the collective that reads `send`
+            with torch.cuda.stream(side):
+                self.res = self.fes[lane].run(batch, K=K, records=rows, pair_id0=self.lo)
         if j == self.sets - 1:                      # the batch's last launch set
-            if self.pipelined and self.world > 1:
+            if self.lanes > 1:
+                import torch
+
+                for side in self._side[:min(self.lanes, self.sets) - 1]:
+                    torch.cuda.current_stream(self.dev).wait_stream(side)
+            if self._kernels_only:
+                pass
+            elif self.pipelined and self.world > 1:
                 self._pending = True                # gathered inside the next batch (or by flush())
             else:
                 self.gather.all_gather()
@@ -254,8 +283,11 @@ class ShardedFrontend:
                 self._work = None
         if not self.gather_in_graph:
             with torch.cuda.graph(g):
-                for j, b in enumerate(batches):
-                    self.res = self.fe.run(b, K=K, records=self.send[j * self.cap: j * self.cap + b.n_pairs], pair_id0=self.lo)
+                self._k, self._kernels_only = 0, True          # step() then issues no collective
+                try:
+                    body()
+                finally:
+                    self._kernels_only = False
         self._k = 0
         self._pending = self.pipelined and self.world > 1     # the eager pass left a complete batch in `send`
         self._graph = g

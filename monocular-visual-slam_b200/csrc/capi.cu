@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
   double d[8];
   float f[8], g[8];
   unsigned long long p2[8];
+  float2 q2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     x[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
     f[k] = 1.0f + 1e-7f * (float)(x[k] & 1023);
     g[k] = 1.0f - 1e-7f * (float)(x[k] & 511);
     p2[k] = ((unsigned long long)__float_as_uint(f[k]) << 32) | __float_as_uint(f[k] * 0.5f);
+    q2[k] = make_float2(f[k] * 0.25f, g[k] * 0.125f);
   }
   const uint32_t c1 = blockIdx.x | 1u, c2 = threadIdx.x | 3u;
   for (int it = 0; it < iters; ++it) {
@@ -118,12 +120,17 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, uint32_t* sink) {
         if (WHICH == 19) {  // FFMA2 with three distinct 64-bit sources (register-file read bandwidth)
           asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p2[k]) : "l"(p2[(k + 1) & 7]), "l"(p2[(k + 2) & 7]));
         }
+        if (WHICH == 20) q2[k] = __ffma2_rn(make_float2(f[k], f[k]), q2[(k + 1) & 7], q2[k]);               // (scalar, pair, pair)
+        if (WHICH == 21) q2[k] = __ffma2_rn(make_float2(f[k], f[k]), q2[k], make_float2(g[k], g[k]));       // (scalar, pair, scalar)
+        if (WHICH == 22) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k]) : "f"(g[k]), "f"(f[(k + 1) & 7]));   // scalar FFMA, three distinct sources
+        if (WHICH == 23) q2[k] = __ffma2_rn(q2[k], q2[k], q2[(k + 1) & 7]);                                 // (pair, same pair, pair)
+        if (WHICH == 24) q2[k] = __ffma2_rn(make_float2(f[k], f[k]), q2[k], q2[k]);                         // (scalar, pair, same pair)
       }
     }
   }
   uint32_t acc = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc ^= x[k] ^ (uint32_t)__double_as_longlong(d[k]) ^ __float_as_uint(f[k]) ^ (uint32_t)p2[k] ^ (uint32_t)(p2[k] >> 32) ^ __float_as_uint(g[k]);
+  for (int k = 0; k < 8; ++k) acc ^= x[k] ^ (uint32_t)__double_as_longlong(d[k]) ^ __float_as_uint(f[k]) ^ (uint32_t)p2[k] ^ (uint32_t)(p2[k] >> 32) ^ __float_as_uint(g[k]) ^ __float_as_uint(q2[k].x) ^ __float_as_uint(q2[k].y);
   if (acc == 0x12345678u) sink[0] = acc;  // keeps the chains alive, practically never taken
 }
 
@@ -239,7 +246,7 @@ int b2s_tmem_microbench(int iters, int warps, double* bytes_out, uint32_t* sink,
 
 int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, uint32_t* sink, void* stream) {
   using namespace b2s;
-  B2S_REQUIRE(which >= 0 && which <= 19, "which must be 0..19");
+  B2S_REQUIRE(which >= 0 && which <= 24, "which must be 0..24");
   B2S_REQUIRE(iters > 0 && ctas_per_sm > 0 && sink, "bad argument");
   const int grid = sm_count() * ctas_per_sm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -262,6 +269,11 @@ int b2s_pipe_microbench(int which, int iters, int ctas_per_sm, double* ops_out, 
     case 17: pipe_kernel<17><<<grid, 256, 0, st>>>(iters, sink); break;
     case 18: pipe_kernel<18><<<grid, 256, 0, st>>>(iters, sink); break;
     case 19: pipe_kernel<19><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 20: pipe_kernel<20><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 21: pipe_kernel<21><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 22: pipe_kernel<22><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 23: pipe_kernel<23><<<grid, 256, 0, st>>>(iters, sink); break;
+    case 24: pipe_kernel<24><<<grid, 256, 0, st>>>(iters, sink); break;
     case 16: pipe_kernel<16><<<grid, 256, 0, st>>>(iters, sink); break;
     default: pipe_kernel<6><<<grid, 256, 0, st>>>(iters, sink); break;
   }

@@ -164,7 +164,38 @@ def test_sharded_frontend_world1_graph_equals_eager_frontend():
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)
 
 
-@pytest.mark.parametrize("config", [3, 5])
+def test_sharded_frontend_lanes_equal_single_stream():
+    """A batch of 5 launch sets alternating over 3 streams (own workspaces per lane, fork / join inside the captured
+    graph) writes the records the single-stream schedule writes, eagerly and replayed."""
+    import torch
+    from b200slam.frontend import FrontendConfig
+    from b200slam.sharding import ShardedFrontend
+    S = 300
+    bl = [_seq_batch(9, 700, 60 + j)[0] for j in range(5)]
+    cfg = FrontendConfig(hypotheses=256, max_matches=S, with_pose=True)
+    got = {}
+    for lanes in (1, 3):
+        sf = ShardedFrontend(cfg, bl[0].n_pairs, sets_per_gather=5, lanes=lanes)
+        assert sf.lanes == lanes
+        for b in bl:
+            sf.step(b)
+        sf.flush()
+        torch.cuda.synchronize()
+        eager = sf.records().clone()
+        sf.capture(bl)
+        sf.gather.buf.zero_()
+        for _ in range(2):
+            sf.replay()
+        sf.flush()
+        torch.cuda.synchronize()
+        assert torch.equal(sf.records(), eager)
+        got[lanes] = eager
+        sf.close()
+    assert torch.equal(got[1], got[3])
+    assert len({bytes(got[1][j].cpu().numpy().tobytes()) for j in range(5)}) == 5      # five different launch sets
+
+
+@pytest.mark.parametrize("config", [2, 3, 5])
 def test_two_gpus_equal_one_gpu(config, tmp_path):
     """world_size 2 over NCCL (torchrun): the gathered records of the pair-sharded loop-closure batch (config #3
     shape, small) and of the keyframe-sharded sweep (config #5 shape, small) equal the 1-GPU run bit for bit."""

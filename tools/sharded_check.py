@@ -50,6 +50,26 @@ if a.config == 3:
     torch.cuda.synchronize()
     u = unpack_records(sf.records()[0].cpu().numpy(), S)
     out = {k: v for k, v in u.items()}
+elif a.config == 2:
+    # a batch of 5 launch sets (alternating over the stream lanes), ONE pipelined collective per batch
+    n, sets = 21, 5
+    sf = ShardedFrontend(cfg, n, sets_per_gather=sets)
+    lo, hi = sf.lo, sf.hi
+    bl = []
+    for j in range(sets):
+        qs, ts, kq, kt = tracking_pairs(n, 500, seed=50 + j, keep=0.4, ragged=True)
+        bl.append(PairBatch.from_host(qs[lo:hi], ts[lo:hi], kq[lo:hi], kt[lo:hi]))
+    in_graph = sf.capture(bl, collective_in_graph=not a.no_graph_collective)
+    print(f"[rank {rank}] captured, collective_in_graph={in_graph}, lanes={sf.lanes}", file=sys.stderr, flush=True)
+    for _ in range(3):
+        sf.replay()
+    sf.flush()
+    torch.cuda.synchronize()
+    rec = sf.records().cpu().numpy()
+    for j in range(sets):
+        for k, v in unpack_records(rec[j], S).items():
+            out[f"set{j}/{k}"] = v
+    out["n_matches"], out["inliers"], out["pair_id"] = out["set0/n_matches"], out["set0/inliers"], out["set0/pair_id"]
 else:
     rng = np.random.default_rng(9)
     n_kf = 31
