@@ -193,6 +193,43 @@ def test_hybrid_scoring_equals_float64_everywhere(rg, R):
     assert total_band == len(cases)
 
 
+def test_hybrid_scoring_ragged_counts_equal_float64_and_numpy(R):
+    """The packed (two correspondences per instruction) loop on every count around its group sizes (32-evaluation groups,
+    64-evaluation spans, 512-correspondence chunks), in ONE ragged batch with an empty pair, thresholds on residuals of
+    the last correspondences (band hits in the padded tail group), whole and sliced over the correspondences (max_m)."""
+    import torch
+    rng = np.random.default_rng(6464)
+    Ms = [0, 1, 2, 8, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 500, 511, 512, 513, 575, 576, 577, 1024 + 33, 2000]
+    H = 130                                                        # two CTAs of hypotheses, the second with dead lanes
+    src = [rng.uniform(-1, 1, (m, 2)).astype(np.float32) for m in Ms]
+    dst = [(s_ + rng.normal(0, 0.01, s_.shape)).astype(np.float32) for s_ in src]
+    Es = rng.normal(size=(len(Ms), H, 9))
+    corr = torch.from_numpy(np.vstack([np.hstack([a, b]) for a, b in zip(src, dst)]).astype(np.float32)).cuda()
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(Ms)]).astype(np.int32)).cuda()
+    cnt = torch.tensor(Ms, dtype=torch.int32, device="cuda")
+    th2 = np.full(len(Ms), 1e-4)
+    for p, m in enumerate(Ms):                                     # the exact residual of the LAST correspondence under hypothesis 3
+        if m:
+            h = lambda a: np.hstack([a, np.ones((len(a), 1))]).astype(np.float64)
+            with np.errstate(all="ignore"):
+                e = ro.sampson_sq_err(Es[p, 3].reshape(3, 3), h(src[p][-1:]), h(dst[p][-1:]))
+            if np.isfinite(e[0]) and e[0] > 0:
+                th2[p] = e[0]
+    E = torch.from_numpy(np.ascontiguousarray(Es)).cuda()
+    tpp = torch.from_numpy(th2).cuda()
+    ref = R.score(corr, off, cnt, len(Ms), E, 1e-4, th2_per_pair=tpp, precision=6464).cpu().numpy()
+    for max_m in (0, max(Ms)):
+        got = R.score(corr, off, cnt, len(Ms), E, 1e-4, th2_per_pair=tpp, precision=64, max_m=max_m).cpu().numpy()
+        np.testing.assert_array_equal(got, ref, err_msg=f"max_m={max_m}")
+    assert not ref[0].any()
+    for p in (3, 9, 16, 19):                                       # NumPy float64 on a few pairs (boundary evaluations may flip: tolerance)
+        h = lambda a: np.hstack([a, np.ones((len(a), 1))]).astype(np.float64)
+        for hyp in (0, 3, 129):
+            with np.errstate(all="ignore"):
+                want = int(np.sum(ro.sampson_sq_err(Es[p, hyp].reshape(3, 3), h(src[p]), h(dst[p])) < th2[p]))
+            assert abs(int(ref[p, hyp]) - want) <= max(1, int(FLIP_TOL * Ms[p])), (p, hyp)
+
+
 def test_tensor_core_scoring_equals_float64(rg, R):
     """K3t (tcgen05 kind::tf32, hi/lo-split operands): (1) its raw accumulators stay inside the
     error bound the kernel assumes (kappa * ||coefficients|| * ||monomials||, measured here with a
