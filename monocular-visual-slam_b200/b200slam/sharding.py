@@ -191,6 +191,7 @@ class ShardedFrontend:
             self.send = self.gather.local               # in-place: the send slice of the gather buffer itself
         self.lo, self.hi = shard_bounds(self.n_pairs_global, self.rank, self.world)
         self._work, self._k, self._pending, self._kernels_only = None, 0, False, False
+        self._held = []
         self._graph, self.res = None, None
         self.gather_in_graph = False
 
@@ -228,12 +229,16 @@ class ShardedFrontend:
                 side.wait_stream(torch.cuda.current_stream(self.dev))   # included, i.e. behind the join of the collective that reads `send`
             with torch.cuda.stream(side):
                 self.res = self.fes[lane].run(batch, K=K, records=rows, pair_id0=self.lo)
+            # the caller's stream is ordered behind this lane only at the batch's join: keep the inputs alive until
+            # then, so that memory the caller frees early is not handed out again while the lane still reads it
+            self._held.append((batch, K))
         if j == self.sets - 1:                      # the batch's last launch set
             if self.lanes > 1:
                 import torch
 
                 for side in self._side[:min(self.lanes, self.sets) - 1]:
                     torch.cuda.current_stream(self.dev).wait_stream(side)
+                self._held.clear()
             if self._kernels_only:
                 pass
             elif self.pipelined and self.world > 1:
