@@ -1,7 +1,7 @@
 """Per-kernel SASS evidence of the built library (no GPU needed): for every kernel of libb2s.so the counts of the
 Blackwell-specific instructions — UTCIMMA / UTCHMMA / UTCQMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTCBAR
 (tcgen05.commit), UBLKCP (cp.async.bulk), UTMALDG (tensor-map TMA), SYNCS (mbarrier), POPC, REDUX, VIMNMX*,
-DFMA, FFMA — plus registers / spills from the ptxas logs.  Writes profiles/<round>_sass.md and a trimmed listing of
+DFMA, FFMA2 / FMUL2 (packed fma.rn.f32x2), FFMA — plus registers / spills from the ptxas logs.  Writes profiles/<round>_sass.md and a trimmed listing of
 the shipped Hamming kernel's tcgen05 lines.   Usage: python tools/sass_evidence.py r02"""
 import collections
 import re
@@ -12,7 +12,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "monocular-visual-slam_b200" / "b200slam" / "libb2s.so"
 OPS = ("UTCIMMA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "SYNCS", "POPC", "REDUX", "VIMNMX3", "VIMNMX", "VIADDMNMX",
-       "DFMA", "FFMA", "SHFL", "ATOMG", "LDS", "STS")
+       "DFMA", "FFMA2", "FMUL2", "FFMA", "SHFL", "ATOMG", "LDS", "STS")
 
 
 def kernels():
@@ -64,10 +64,10 @@ def main():
     for short, c, _ in sorted(rows, key=lambda r: -r[1]["total"]):
         md.append(f"| `{short}` | {c['total']} | " + " | ".join(str(c[o]) if c[o] else "" for o in OPS) + " |")
     # trimmed listing of the shipped Hamming kernel
-    target = [r for r in rows if "hamming_knn2_i8s_kernel<1, false, 2>" in r[0]]
+    target = [r for r in rows if "hamming_knn2_i8s_kernel<1, false, 2, true>" in r[0]]
     if target:
         _, _, mangled = target[0]
-        md += ["", "## `hamming_knn2_i8s_kernel<1, false, 2>` — every tensor-core / TMEM / bulk-copy line", "", "```"]
+        md += ["", "## `hamming_knn2_i8s_kernel<1, false, 2, true>` (shipped) — every tensor-core / TMEM / bulk-copy line", "", "```"]
         md += [l.split("*/", 1)[0].strip() + "*/ " + re.sub(r"\s*/\*.*", "", l.split("*/", 1)[1]).strip()
                for l in ks[mangled] if re.search(r"UTCIMMA|LDTM|UTCBAR|UBLKCP|UTCATOM|ELECT", l)]
         md += ["```"]
