@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(
 //       |d - fl(d)| <= 2 |num| delta + delta^2 + 6u th^2 nE^2 (W1^2 + W2^2) + 7u (num^2 + T)
 //   (all to first order in u; the float64 kernel's own rounding is 9 orders of magnitude below).
 //   B below takes 7u, 9u and 10u for the 5u, 6u and 7u (1.4x), and every norm is nudged up by 1e-4.
-constexpr int kScoreHThreads = 128;
+#ifndef B2S_K3H_THREADS
+#define B2S_K3H_THREADS 128
+#endif
+constexpr int kScoreHThreads = B2S_K3H_THREADS;
 constexpr int kScoreHChunk = 512;   // 8 KB of shared memory: the usual pair (<= 500 correspondences) is staged once, in the pass that also finds W1 / W2
 
 // B2S_K3H_PACK2: a thread evaluates TWO correspondences per step on packed fma.rn.f32x2 (SASS FFMA2): the same 19
@@ -747,6 +750,7 @@ int b2s_ransac_score_batched(const float* corr, const int32_t* c_off, const int3
   const float4* c4 = reinterpret_cast<const float4*>(corr);
   if (precision == 64) {
     // few pairs with many correspondences each: slice the correspondences too (see the kernel)
+    grid.x = (H + kScoreHThreads - 1) / kScoreHThreads;
     const long blocks = (long)grid.x * grid.y, sms = sm_count();
     int zs = 1;
     if (max_m > 2 * kScoreHChunk && blocks < sms) {
